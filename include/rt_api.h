@@ -1,0 +1,238 @@
+/*
+ * rt_api.h — C-ABI of the B200 rendering hot path (libpytracer_b200.so).
+ *
+ * The reference (ziotom78/pytracer) is pure Python and has no FFI: the seam this
+ * library plugs into is the duck-typed call
+ *     ImageTracer.fire_all_rays(func)              src/pytracer/imagetracer.py:60-110
+ * with `func` one of the Renderer callables         src/pytracer/render.py:26-193.
+ * One rt_render() call replaces the whole descent fire_all_rays -> Camera.fire_ray ->
+ * Renderer.__call__ -> World.ray_intersection -> Shape/BRDF/Pigment/PCG for every pixel.
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions: plain C structs of fixed-width types; every function returns 0 on success
+ * and a negative code on failure (text via rt_last_error(), thread-local); no exception
+ * crosses the ABI; the caller owns every buffer it passes; matrices are row-major 3x4
+ * affine blocks (the first three rows of the reference's 4x4 lists) in fp64 — the library
+ * derives its own fp32 mirrors. Image buffers are [height][width][3], row 0 = TOP of the
+ * image, exactly HdrImage.pixel_offset (src/pytracer/hdrimages.py:78-80).
+ */
+#ifndef PYTRACER_B200_RT_API_H
+#define PYTRACER_B200_RT_API_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_API_VERSION 1
+
+/* Shape.kind: Sphere shapes.py:88, Plane shapes.py:154 */
+enum { RT_SHAPE_SPHERE = 0, RT_SHAPE_PLANE = 1 };
+/* DiffuseBRDF materials.py:123, SpecularBRDF materials.py:155 */
+enum { RT_BRDF_DIFFUSE = 0, RT_BRDF_SPECULAR = 1 };
+/* UniformPigment materials.py:50, CheckeredPigment :85, ImagePigment :62 */
+enum { RT_PIGMENT_UNIFORM = 0, RT_PIGMENT_CHECKERED = 1, RT_PIGMENT_IMAGE = 2 };
+/* OrthogonalCamera camera.py:42, PerspectiveCamera camera.py:82 */
+enum { RT_CAMERA_ORTHOGONAL = 0, RT_CAMERA_PERSPECTIVE = 1 };
+/* main.py:73 RENDERERS, in the reference's order */
+enum { RT_ALGO_ONOFF = 0, RT_ALGO_FLAT = 1, RT_ALGO_PATHTRACING = 2, RT_ALGO_POINTLIGHT = 3 };
+
+/* Arithmetic type of the traced path. AUTO = F64 for the deterministic renderers (their
+ * hit index must be bit-exact against the fp64 reference), F32 for path tracing. */
+enum { RT_PRECISION_AUTO = 0, RT_PRECISION_F32 = 1, RT_PRECISION_F64 = 2 };
+
+/* Path-tracer kernel. MEGA = one thread per pixel-sample walking the recursion of
+ * render.py:99-139 depth-first in the reference's own order; WARP = warp-cooperative
+ * wavefront: 32 lanes drain a shared-memory stack of scatter records, children compacted
+ * with ballots so that lanes stay full whatever the branching of single samples. */
+enum { RT_VARIANT_AUTO = 0, RT_VARIANT_MEGA = 1, RT_VARIANT_WARP = 2 };
+
+/* How the scatter/roulette random numbers are organised (path tracing only).
+ * STREAMS: sample k owns PCG(init_state = pt_state, init_seq = (pt_inc >> 1) + k): the
+ *          image does not depend on how samples are spread over threads or GPUs.
+ * REPLAY : sample k starts from replay_states[k] with increment pt_inc and draws in the
+ *          reference's order (MEGA variant only). Feeding the states the sequential
+ *          reference stream has at the start of every sample reproduces the reference
+ *          image itself, not just its distribution. */
+enum { RT_RNG_STREAMS = 0, RT_RNG_REPLAY = 1 };
+
+/* Multi-GPU partition of one image. SPP: rank r traces the strata s with
+ * s % part_count == r of every pixel; ROWS: rank r traces the rows y with
+ * y % part_count == r (interleaved: cost per row varies 1..85 rays/sample on demo.txt).
+ * Every rank writes a full-size image holding its share (already scaled by 1/S^2; rows it
+ * does not own are zero), so one sum over ranks is the final image. */
+enum { RT_PART_NONE = 0, RT_PART_SPP = 1, RT_PART_ROWS = 2 };
+
+enum {
+  RT_OK = 0,
+  RT_ERR_INVALID = -1,   /* bad argument / unsupported combination */
+  RT_ERR_CUDA = -2,      /* CUDA runtime error, text in rt_last_error() */
+  RT_ERR_NO_DEVICE = -3, /* no CUDA device: there is no CPU fallback */
+  RT_ERR_OVERFLOW = -4   /* device-side work stack overflow (reported, never silent) */
+};
+
+/* Pigment.get_color, materials.py:58 / :70-82 / :96-100 */
+typedef struct rt_pigment {
+  int32_t kind;
+  int32_t num_of_steps;   /* checkered */
+  int32_t tex_width;      /* image */
+  int32_t tex_height;
+  int64_t tex_offset;     /* first texel of this image inside rt_scene_desc.texels, in texels */
+  double color1[3];       /* uniform: the colour; checkered: color1 */
+  double color2[3];       /* checkered: color2 */
+} rt_pigment;
+
+/* Material, materials.py:199-204 */
+typedef struct rt_material {
+  int32_t brdf_kind;
+  int32_t brdf_pigment;     /* index into pigments */
+  int32_t emitted_pigment;  /* index into pigments */
+  int32_t _pad;
+  double threshold_angle_rad; /* SpecularBRDF.eval only, materials.py:158-173 */
+} rt_material;
+
+/* PointLight, lights.py:25-39 */
+typedef struct rt_light {
+  double position[3];
+  double color[3];
+  double linear_radius;
+} rt_light;
+
+/* World (world.py:36-49) flattened; shapes keep the order of World.shapes because
+ * ray_intersection lets the FIRST shape win ties (world.py:62, strict '<'). */
+typedef struct rt_scene_desc {
+  int32_t n_shapes;
+  int32_t n_materials;
+  int32_t n_pigments;
+  int32_t n_lights;
+  const int32_t* shape_kind;      /* [n_shapes] */
+  const int32_t* shape_material;  /* [n_shapes] index into materials */
+  const double* shape_m;          /* [n_shapes][12] Transformation.m rows 0..2 */
+  const double* shape_invm;       /* [n_shapes][12] Transformation.invm rows 0..2 */
+  const rt_material* materials;
+  const rt_pigment* pigments;
+  const rt_light* lights;
+  int64_t n_texels;
+  const double* texels;           /* [n_texels][3] RGB, image rows top to bottom (HdrImage.pixels order) */
+} rt_scene_desc;
+
+/* Camera, camera.py:42-124 */
+typedef struct rt_camera {
+  int32_t kind;
+  int32_t _pad;
+  double screen_distance; /* perspective only */
+  double aspect_ratio;
+  double m[12];           /* camera Transformation.m rows 0..2 */
+} rt_camera;
+
+typedef struct rt_render_params {
+  int32_t width;
+  int32_t height;
+  int32_t samples_per_side; /* 0 = one ray through the pixel centre, no RNG (imagetracer.py:103) */
+  int32_t algorithm;
+  rt_camera camera;
+  double background[3];     /* Renderer.background_color */
+  double onoff_color[3];    /* OnOffRenderer.color */
+  double ambient[3];        /* PointLightRenderer.ambient_color */
+  int32_t num_of_rays;      /* PathTracer */
+  int32_t max_depth;
+  int32_t rr_limit;         /* PathTracer.russian_roulette_limit */
+  int32_t rng_mode;
+  /* ImageTracer.pcg as it is when fire_all_rays starts: sample k (row-major pixels, then
+   * strata rows, then strata columns) uses draws 2k and 2k+1 of this stream, u before v
+   * (imagetracer.py:88-93). The device jumps ahead instead of drawing sequentially. */
+  uint64_t aa_state;
+  uint64_t aa_inc;
+  /* PathTracer.pcg as it is when fire_all_rays starts (see RT_RNG_*). */
+  uint64_t pt_state;
+  uint64_t pt_inc;
+  const uint64_t* replay_states; /* HOST pointer, [width*height*max(1,S)^2], RT_RNG_REPLAY only */
+  int32_t part_mode;
+  int32_t part_rank;
+  int32_t part_count;
+  int32_t variant;
+  int32_t precision;
+  int32_t out_f64;          /* 1: out_rgb is double[H][W][3] instead of float */
+} rt_render_params;
+
+typedef struct rt_stats {
+  uint64_t rays_closest;  /* World.ray_intersection calls, world.py:51 */
+  uint64_t rays_shadow;   /* World.is_point_visible calls, world.py:71 */
+  uint64_t samples;       /* Renderer.__call__ invocations from fire_all_rays */
+  float kernel_ms;        /* CUDA events around the render kernels, on the launch stream */
+  float total_ms;         /* kernel_ms + device->host copy when the call does one */
+  int32_t variant_used;
+  int32_t precision_used;
+  int32_t n_launches;     /* kernels of this library launched by the call */
+  int32_t overflow;       /* non-zero: a warp work stack overflowed, image is invalid */
+} rt_stats;
+
+/* One closest hit, mirrors HitRecord (hitrecord.py:27-46) + the index World's loop would report */
+typedef struct rt_hit {
+  int32_t shape;          /* index in World.shapes, -1 = miss */
+  int32_t material;
+  double t;
+  double world_point[3];
+  double normal[3];       /* normalised, as World.ray_intersection returns it (world.py:66-67) */
+  double uv[2];
+} rt_hit;
+
+typedef struct rt_scene rt_scene;
+
+/* ---- device / errors ---- */
+int rt_api_version(void);
+int rt_device_count(void);
+int rt_set_device(int device);
+const char* rt_last_error(void);
+
+/* ---- scene: replaces the object graph walked by World.ray_intersection ---- */
+int rt_scene_create(const rt_scene_desc* desc, rt_scene** out);
+void rt_scene_destroy(rt_scene* scene);
+
+/* ---- the hot path: ImageTracer.fire_all_rays(renderer) ---- */
+/* Host buffers: out_rgb float[H][W][3] (or double if out_f64), out_hit_index int32[H][W]
+ * (optional; shape hit by the LAST sample of each pixel, -1 = miss). Blocking. */
+int rt_render(rt_scene* scene, const rt_render_params* params, void* out_rgb,
+              int32_t* out_hit_index, rt_stats* stats);
+/* Same with DEVICE buffers on a caller stream (cudaStream_t passed as void*; NULL = default
+ * stream). Returns after enqueueing; call rt_render_finish() to synchronise the stream and
+ * collect the counters. */
+int rt_render_device(rt_scene* scene, const rt_render_params* params, void* d_out_rgb,
+                     int32_t* d_out_hit_index, void* stream);
+int rt_render_finish(rt_scene* scene, void* stream, rt_stats* stats);
+
+/* ---- Renderer.__call__(ray) for explicit rays (render.py:52,65,99,157) ----
+ * rays: double[n][8] = origin xyz, dir xyz, tmin, tmax; depth int32[n] (NULL = 0).
+ * pcg_state_inc: {state, inc} of PathTracer.pcg, read and written back (rays are traced
+ * one after the other on ONE stream in the reference's draw order). */
+int rt_trace_rays(rt_scene* scene, const rt_render_params* params, const double* rays,
+                  const int32_t* depth, int32_t n, uint64_t* pcg_state_inc, double* out_rgb);
+
+/* ---- probes used by the known-answer tests (one per reference function) ---- */
+/* World.ray_intersection, world.py:51-69 */
+int rt_intersect(rt_scene* scene, int32_t precision, const double* rays, int32_t n, rt_hit* out);
+/* World.is_point_visible(point, observer_pos), world.py:71-80; pairs double[n][6] = point, observer */
+int rt_is_point_visible(rt_scene* scene, int32_t precision, const double* pairs, int32_t n,
+                        uint8_t* out);
+/* ImageTracer.fire_ray for every sample of the image, in sample order; out double[n][8] */
+int rt_camera_rays(const rt_render_params* params, int32_t precision, double* out_rays);
+/* PCG.random, pcg.py:43-58: n draws from {state, inc}; state_inc is updated */
+int rt_pcg_draw(uint64_t* state_inc, int32_t n, uint32_t* out);
+/* PCG.__init__, pcg.py:29-41 evaluated on the device */
+int rt_pcg_seed(uint64_t init_state, uint64_t init_seq, uint64_t* state_inc);
+/* Pigment.get_color: uv double[n][2] -> rgb double[n][3] */
+int rt_pigment_color(rt_scene* scene, int32_t pigment, int32_t precision, const double* uv,
+                     int32_t n, double* out_rgb);
+/* BRDF.scatter_ray (materials.py:132-152, :175-196) for material `material`:
+ * in double[n][9] = incoming dir, interaction point, normal; out rays double[n][8];
+ * draws come sequentially from {state, inc}. */
+int rt_scatter(rt_scene* scene, int32_t material, int32_t precision, const double* in,
+               int32_t n, uint64_t* state_inc, double* out_rays);
+/* create_onb_from_z, geometry.py:247-262: normals double[n][3] -> double[n][9] = e1,e2,e3 */
+int rt_onb(int32_t precision, const double* normals, int32_t n, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
