@@ -210,13 +210,18 @@ int rt_trace_rays(rt_scene* scene, const rt_render_params* params, const double*
                   const int32_t* depth, int32_t n, uint64_t* pcg_state_inc, double* out_rgb);
 
 /* ---- probes used by the known-answer tests (one per reference function) ---- */
-/* World.ray_intersection, world.py:51-69 */
-int rt_intersect(rt_scene* scene, int32_t precision, const double* rays, int32_t n, rt_hit* out);
+/* World.ray_intersection, world.py:51-69 (normalize_normal = 1), or the raw record of the winning
+ * Shape.ray_intersection, shapes.py:97-131 / :163-189 (normalize_normal = 0) */
+int rt_intersect(rt_scene* scene, int32_t precision, int32_t normalize_normal, const double* rays,
+                 int32_t n, rt_hit* out);
 /* World.is_point_visible(point, observer_pos), world.py:71-80; pairs double[n][6] = point, observer */
 int rt_is_point_visible(rt_scene* scene, int32_t precision, const double* pairs, int32_t n,
                         uint8_t* out);
 /* ImageTracer.fire_ray for every sample of the image, in sample order; out double[n][8] */
 int rt_camera_rays(const rt_render_params* params, int32_t precision, double* out_rays);
+/* Camera.fire_ray(u, v), camera.py:59-78 / :103-124: uv double[n][2] -> rays double[n][8] */
+int rt_camera_fire(const rt_camera* camera, int32_t precision, const double* uv, int32_t n,
+                   double* out_rays);
 /* PCG.random, pcg.py:43-58: n draws from {state, inc}; state_inc is updated */
 int rt_pcg_draw(uint64_t* state_inc, int32_t n, uint32_t* out);
 /* PCG.__init__, pcg.py:29-41 evaluated on the device */
@@ -231,6 +236,11 @@ int rt_scatter(rt_scene* scene, int32_t material, int32_t precision, const doubl
                int32_t n, uint64_t* state_inc, double* out_rays);
 /* create_onb_from_z, geometry.py:247-262: normals double[n][3] -> double[n][9] = e1,e2,e3 */
 int rt_onb(int32_t precision, const double* normals, int32_t n, double* out);
+
+/* ---- measurement aid: FP32 FMA roofline denominator measured on this device ----
+ * Runs a register-resident FFMA chain kernel (8 independent accumulators per thread, grid sized to
+ * fill every SM) and reports achieved TFLOP/s (2 flops per FMA) and the kernel time. */
+int rt_bench_ffma(int32_t iterations, double* tflops, float* ms);
 
 #ifdef __cplusplus
 }

@@ -51,7 +51,7 @@ def _p(arr: Optional[np.ndarray]):
 
 
 def render(flat, params: _abi.rt_render_params, row_begin: int = 0, row_end: Optional[int] = None,
-           want_hit: bool = True, want_states: bool = False, out: Optional[np.ndarray] = None):
+           want_hit: bool = True, want_states: bool = False, out: Optional[np.ndarray] = None, row_step: int = 1):
     """Sequential fire_all_rays over rows [row_begin, row_end).  Returns a dict with rgb (H,W,3 f64),
     hit_index, counters (closest, shadow, samples), final aa/pt states and per-sample start states."""
     H, W = params.height, params.width
@@ -62,8 +62,9 @@ def render(flat, params: _abi.rt_render_params, row_begin: int = 0, row_end: Opt
     aa = np.array([params.aa_state, params.aa_inc], dtype=np.uint64)
     pt = np.array([params.pt_state, params.pt_inc], dtype=np.uint64)
     spp = max(1, params.samples_per_side) ** 2
-    states = np.zeros((row_end - row_begin) * W * spp, dtype=np.uint64) if want_states else None
-    rc = lib().orc_render(C.byref(flat.desc), C.byref(params), C.c_int(row_begin), C.c_int(row_end),
+    n_rows = len(range(row_begin, row_end, row_step))
+    states = np.zeros(n_rows * W * spp, dtype=np.uint64) if want_states else None
+    rc = lib().orc_render(C.byref(flat.desc), C.byref(params), C.c_int(row_begin), C.c_int(row_end), C.c_int(row_step),
                           _p(rgb), _p(hit), _p(counters), _p(aa), _p(pt), _p(states))
     assert rc == 0
     return dict(rgb=rgb, hit_index=hit, rays_closest=int(counters[0]), rays_shadow=int(counters[1]),
@@ -71,23 +72,20 @@ def render(flat, params: _abi.rt_render_params, row_begin: int = 0, row_end: Opt
 
 
 def render_threaded(flat, params: _abi.rt_render_params, n_threads: int):
-    """CPU-baseline helper: row bands in parallel threads (ctypes drops the GIL).  Each band gets its
-    own jitter/scatter streams, so the image is a different but equally distributed draw; used for
-    timing and for statistical references, never for bit-exact checks."""
+    """CPU-baseline helper: interleaved rows in parallel threads (ctypes drops the GIL).  Each thread
+    gets its own jitter/scatter streams, so the image is a different but equally distributed draw; used
+    for timing and for statistical references, never for bit-exact checks."""
     from pytracer_b200.pcg import PCG
 
     H, W = params.height, params.width
     rgb = np.zeros((H, W, 3), dtype=np.float64)
-    bands = [(H * i // n_threads, H * (i + 1) // n_threads) for i in range(n_threads)]
     results = [None] * n_threads
 
     def work(i):
-        import copy
-
         p = _abi.rt_render_params.from_buffer_copy(bytes(params))
         aa, pt = PCG(params.aa_state & 0xFFFFFFFF, 1000 + i), PCG(params.pt_state & 0xFFFFFFFF, 2000 + i)
         p.aa_state, p.aa_inc, p.pt_state, p.pt_inc = aa.state, aa.inc, pt.state, pt.inc
-        results[i] = render(flat, p, bands[i][0], bands[i][1], want_hit=False, out=rgb)
+        results[i] = render(flat, p, i, H, want_hit=False, out=rgb, row_step=n_threads)
 
     threads = [threading.Thread(target=work, args=(i,)) for i in range(n_threads)]
     for t in threads:

@@ -418,7 +418,9 @@ static ray_t tracer_fire_ray(const rt_render_params* p, int col, int row, double
 }
 
 /*
- * ImageTracer.fire_all_rays (imagetracer.py:60-110) restricted to rows [row_begin,row_end).
+ * ImageTracer.fire_all_rays (imagetracer.py:60-110) restricted to rows row_begin, row_begin +
+ * row_step, ... < row_end (row_step = 1: the reference's loop; > 1: interleaved rows for the
+ * multi-threaded CPU baseline, whose threads must be load-balanced).
  *   rgb          double[H][W][3], only the traced rows are written
  *   hit_index    optional int32[H][W]
  *   counters     uint64[3] = closest-hit queries, shadow queries, samples (accumulated)
@@ -427,7 +429,7 @@ static ray_t tracer_fire_ray(const rt_render_params* p, int col, int row, double
  *                the start of every sample (what RT_RNG_REPLAY consumes)
  */
 int orc_render(const rt_scene_desc* s, const rt_render_params* p, int row_begin, int row_end,
-               double* rgb, int32_t* hit_index, uint64_t* counters, uint64_t* aa_io,
+               int row_step, double* rgb, int32_t* hit_index, uint64_t* counters, uint64_t* aa_io,
                uint64_t* pt_io, uint64_t* sample_states) {
   pcg_t aa = { aa_io[0], aa_io[1] };
   pcg_t pt = { pt_io[0], pt_io[1] };
@@ -435,7 +437,7 @@ int orc_render(const rt_scene_desc* s, const rt_render_params* p, int row_begin,
   ctx_t c = { s, p, &pt, &cnt, -1 };
   int S = p->samples_per_side;
   size_t k = 0;
-  for (int row = row_begin; row < row_end; ++row) {
+  for (int row = row_begin; row < row_end; row += (row_step > 0 ? row_step : 1)) {
     for (int col = 0; col < p->width; ++col) {
       col3 px;
       if (S > 0) {

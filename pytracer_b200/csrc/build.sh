@@ -1,0 +1,15 @@
+#!/bin/bash
+# Builds libpytracer_b200.so for sm_100a (B200) in-tree.  The fp64 kernels are compiled without
+# multiply-add fusion so that they round like the reference's Python arithmetic.
+set -euo pipefail
+cd "$(dirname "$0")"
+OUT=../libpytracer_b200.so
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC"
+mkdir -p build
+nvcc $ARCH $COMMON -c rt_kernels_f32.cu -o build/rt_kernels_f32.o &
+nvcc $ARCH $COMMON --fmad=false -c rt_kernels_f64.cu -o build/rt_kernels_f64.o &
+nvcc $ARCH $COMMON -c rt_api.cu -o build/rt_api.o &
+wait
+nvcc $ARCH -shared -o $OUT build/rt_kernels_f32.o build/rt_kernels_f64.o build/rt_api.o -lcudart_static -lpthread -ldl -lrt
+echo "built $(realpath $OUT)"

@@ -1,0 +1,597 @@
+// rt_api.cu — host side of the C-ABI declared in include/rt_api.h.
+//
+// Owns device memory (scene tables in fp32 and fp64, textures, scratch images, counters), builds
+// the LCG jump table of the jitter stream, picks kernel / precision and launches on the caller's
+// stream.  There is no CPU fallback anywhere: without a CUDA device every entry point fails with
+// RT_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_launch.h"
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+struct rt_scene {
+  int device = 0, sm_count = 0;
+  int n_shapes = 0, n_spheres = 0, n_materials = 0, n_pigments = 0, n_lights = 0;
+  float *invm32 = nullptr, *m32 = nullptr;
+  double *invm64 = nullptr, *m64 = nullptr;
+  int32_t *orig = nullptr, *material = nullptr;
+  DevMaterial* materials = nullptr;
+  DevPigment* pigments = nullptr;
+  DevLight* lights = nullptr;
+  double* texels64 = nullptr;
+  std::vector<cudaArray_t> arrays;
+  std::vector<cudaTextureObject_t> textures;
+  unsigned long long* counters = nullptr;       // device, CNT_SLOTS
+  unsigned long long* counters_host = nullptr;  // pinned
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint64_t* replay = nullptr;
+  size_t replay_cap = 0;
+  void* image = nullptr;  // scratch image for the host-buffer entry point
+  size_t image_cap = 0;
+  int32_t* hit = nullptr;
+  size_t hit_cap = 0;
+  void* probe_buf = nullptr;
+  size_t probe_cap = 0;
+  LaunchInfo last_info = {0, 0};
+  int last_precision = 0;
+  bool pending = false;
+};
+
+extern "C" int rt_api_version(void) { return RT_API_VERSION; }
+
+extern "C" const char* rt_last_error(void) { return g_err; }
+
+extern "C" int rt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int rt_set_device(int device) {
+  if (rt_device_count() <= 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
+  CU(cudaSetDevice(device));
+  return RT_OK;
+}
+
+template <typename T> static SceneView<T> view_of(const rt_scene* s);
+template <> SceneView<float> view_of<float>(const rt_scene* s) {
+  SceneView<float> v;
+  v.invm = s->invm32; v.m = s->m32; v.orig = s->orig; v.material = s->material;
+  v.materials = s->materials; v.pigments = s->pigments; v.lights = s->lights;
+  v.n_shapes = s->n_shapes; v.n_spheres = s->n_spheres; v.n_lights = s->n_lights;
+  return v;
+}
+template <> SceneView<double> view_of<double>(const rt_scene* s) {
+  SceneView<double> v;
+  v.invm = s->invm64; v.m = s->m64; v.orig = s->orig; v.material = s->material;
+  v.materials = s->materials; v.pigments = s->pigments; v.lights = s->lights;
+  v.n_shapes = s->n_shapes; v.n_spheres = s->n_spheres; v.n_lights = s->n_lights;
+  return v;
+}
+
+template <typename T> static int upload(T** dst, const std::vector<T>& src) {
+  size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+  CU(cudaMalloc((void**)dst, bytes));
+  if (!src.empty()) CU(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return RT_OK;
+}
+
+extern "C" void rt_scene_destroy(rt_scene* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  for (auto t : s->textures) cudaDestroyTextureObject(t);
+  for (auto a : s->arrays) cudaFreeArray(a);
+  cudaFree(s->invm32); cudaFree(s->m32); cudaFree(s->invm64); cudaFree(s->m64);
+  cudaFree(s->orig); cudaFree(s->material); cudaFree(s->materials); cudaFree(s->pigments);
+  cudaFree(s->lights); cudaFree(s->texels64); cudaFree(s->counters); cudaFree(s->replay);
+  cudaFree(s->image); cudaFree(s->hit); cudaFree(s->probe_buf);
+  if (s->counters_host) cudaFreeHost(s->counters_host);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  delete s;
+}
+
+extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
+  if (!d || !out) return fail(RT_ERR_INVALID, "rt_scene_create: null argument");
+  if (rt_device_count() <= 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
+  if (d->n_shapes < 0 || d->n_materials < 0 || d->n_pigments < 0 || d->n_lights < 0)
+    return fail(RT_ERR_INVALID, "rt_scene_create: negative count");
+  rt_scene* s = new rt_scene();
+  *out = nullptr;
+  cudaGetDevice(&s->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, s->device) != cudaSuccess) { delete s; return fail(RT_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+  s->sm_count = prop.multiProcessorCount;
+  s->n_shapes = d->n_shapes; s->n_materials = d->n_materials; s->n_pigments = d->n_pigments; s->n_lights = d->n_lights;
+
+  // ---- shapes, sorted spheres first / planes after, World.shapes order kept inside each group
+  std::vector<int> order;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < d->n_shapes; ++i) {
+      int k = d->shape_kind[i];
+      if (k != RT_SHAPE_SPHERE && k != RT_SHAPE_PLANE) { delete s; return fail(RT_ERR_INVALID, "shape %d: unknown kind %d", i, k); }
+      if ((pass == 0) == (k == RT_SHAPE_SPHERE)) order.push_back(i);
+    }
+  std::vector<float> invm32, m32;
+  std::vector<double> invm64, m64;
+  std::vector<int32_t> orig, mat;
+  for (int i : order) {
+    if (d->shape_kind[i] == RT_SHAPE_SPHERE) s->n_spheres++;
+    int mi = d->shape_material[i];
+    if (mi < 0 || mi >= d->n_materials) { delete s; return fail(RT_ERR_INVALID, "shape %d: material index %d out of range", i, mi); }
+    orig.push_back(i);
+    mat.push_back(mi);
+    for (int k = 0; k < 12; ++k) {
+      double a = d->shape_invm[12 * (size_t)i + k], b = d->shape_m[12 * (size_t)i + k];
+      invm64.push_back(a); m64.push_back(b);
+      invm32.push_back((float)a); m32.push_back((float)b);
+    }
+  }
+  int rc;
+#define UP(field, vec) if ((rc = upload(&s->field, vec)) != RT_OK) { rt_scene_destroy(s); return rc; }
+  UP(invm32, invm32) UP(m32, m32) UP(invm64, invm64) UP(m64, m64) UP(orig, orig) UP(material, mat)
+
+  // ---- textures: fp64 copy for the fp64 path, float4 CUDA arrays behind texture objects for fp32
+  std::vector<double> tex64;
+  if (d->n_texels > 0) tex64.assign(d->texels, d->texels + 3 * (size_t)d->n_texels);
+  UP(texels64, tex64)
+  std::vector<DevPigment> pigs(d->n_pigments);
+  for (int i = 0; i < d->n_pigments; ++i) {
+    const rt_pigment& p = d->pigments[i];
+    DevPigment& q = pigs[i];
+    memset(&q, 0, sizeof(q));
+    q.kind = p.kind; q.steps = p.num_of_steps; q.tex_w = p.tex_width; q.tex_h = p.tex_height;
+    for (int k = 0; k < 3; ++k) {
+      q.c1d[k] = p.color1[k]; q.c2d[k] = p.color2[k];
+      q.c1[k] = (float)p.color1[k]; q.c2[k] = (float)p.color2[k];
+    }
+    if (p.kind == RT_PIGMENT_IMAGE) {
+      if (p.tex_width <= 0 || p.tex_height <= 0 || p.tex_offset < 0 ||
+          p.tex_offset + (int64_t)p.tex_width * p.tex_height > d->n_texels) {
+        rt_scene_destroy(s);
+        return fail(RT_ERR_INVALID, "pigment %d: texture window outside the texel buffer", i);
+      }
+      q.texels64 = s->texels64 + 3 * (size_t)p.tex_offset;
+      std::vector<float4> texels((size_t)p.tex_width * p.tex_height);
+      const double* src = d->texels + 3 * (size_t)p.tex_offset;
+      for (size_t t = 0; t < texels.size(); ++t)
+        texels[t] = make_float4((float)src[3 * t], (float)src[3 * t + 1], (float)src[3 * t + 2], 0.f);
+      cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float4>();
+      cudaArray_t arr = nullptr;
+      cudaError_t e = cudaMallocArray(&arr, &fmt, p.tex_width, p.tex_height);
+      if (e == cudaSuccess) {
+        s->arrays.push_back(arr);
+        e = cudaMemcpy2DToArray(arr, 0, 0, texels.data(), p.tex_width * sizeof(float4), p.tex_width * sizeof(float4),
+                                p.tex_height, cudaMemcpyHostToDevice);
+      }
+      cudaTextureObject_t tex = 0;
+      if (e == cudaSuccess) {
+        cudaResourceDesc res;
+        memset(&res, 0, sizeof(res));
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = arr;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        e = cudaCreateTextureObject(&tex, &res, &td, nullptr);
+        if (e == cudaSuccess) s->textures.push_back(tex);
+      }
+      if (e != cudaSuccess) {
+        rt_scene_destroy(s);
+        return fail(RT_ERR_CUDA, "texture for pigment %d: %s", i, cudaGetErrorString(e));
+      }
+      q.tex = tex;
+    } else if (p.kind != RT_PIGMENT_UNIFORM && p.kind != RT_PIGMENT_CHECKERED) {
+      rt_scene_destroy(s);
+      return fail(RT_ERR_INVALID, "pigment %d: unknown kind %d", i, p.kind);
+    }
+  }
+  UP(pigments, pigs)
+  std::vector<DevMaterial> mats(d->n_materials);
+  for (int i = 0; i < d->n_materials; ++i) {
+    const rt_material& m = d->materials[i];
+    if (m.brdf_pigment < 0 || m.brdf_pigment >= d->n_pigments || m.emitted_pigment < 0 || m.emitted_pigment >= d->n_pigments ||
+        (m.brdf_kind != RT_BRDF_DIFFUSE && m.brdf_kind != RT_BRDF_SPECULAR)) {
+      rt_scene_destroy(s);
+      return fail(RT_ERR_INVALID, "material %d: bad BRDF kind or pigment index", i);
+    }
+    mats[i].brdf_kind = m.brdf_kind; mats[i].brdf_pigment = m.brdf_pigment; mats[i].emitted_pigment = m.emitted_pigment;
+    mats[i]._pad = 0; mats[i].threshold = m.threshold_angle_rad;
+  }
+  UP(materials, mats)
+  std::vector<DevLight> lights(d->n_lights);
+  for (int i = 0; i < d->n_lights; ++i) {
+    for (int k = 0; k < 3; ++k) { lights[i].pos[k] = d->lights[i].position[k]; lights[i].color[k] = d->lights[i].color[k]; }
+    lights[i].radius = d->lights[i].linear_radius;
+  }
+  UP(lights, lights)
+#undef UP
+  cudaError_t e = cudaMalloc((void**)&s->counters, CNT_SLOTS * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->counters_host, CNT_SLOTS * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+  if (e != cudaSuccess) { rt_scene_destroy(s); return fail(RT_ERR_CUDA, "scene scratch: %s", cudaGetErrorString(e)); }
+  *out = s;
+  return RT_OK;
+}
+
+// x -> A_b x + C_b = (x -> MULT x + inc) composed 2^b times
+static void build_jump_table(uint64_t inc, JumpTable* t) {
+  uint64_t mult = RT_PCG_MULT, plus = inc;
+  for (int b = 0; b < RT_JUMP_BITS; ++b) {
+    t->mult[b] = mult;
+    t->plus[b] = plus;
+    plus = (mult + 1) * plus;
+    mult = mult * mult;
+  }
+}
+
+static int fill_args(const rt_scene* s, const rt_render_params* p, RenderArgs* a) {
+  if (p->width <= 0 || p->height <= 0) return fail(RT_ERR_INVALID, "image size %dx%d", p->width, p->height);
+  if (p->samples_per_side < 0) return fail(RT_ERR_INVALID, "samples_per_side %d", p->samples_per_side);
+  if (p->algorithm < RT_ALGO_ONOFF || p->algorithm > RT_ALGO_POINTLIGHT) return fail(RT_ERR_INVALID, "algorithm %d", p->algorithm);
+  if (p->camera.kind != RT_CAMERA_ORTHOGONAL && p->camera.kind != RT_CAMERA_PERSPECTIVE) return fail(RT_ERR_INVALID, "camera kind %d", p->camera.kind);
+  if (p->part_mode != RT_PART_NONE && (p->part_count < 1 || p->part_rank < 0 || p->part_rank >= p->part_count))
+    return fail(RT_ERR_INVALID, "partition rank %d of %d", p->part_rank, p->part_count);
+  long long S2 = p->samples_per_side > 0 ? (long long)p->samples_per_side * p->samples_per_side : 1;
+  if ((double)p->width * p->height * (double)S2 * 2.0 >= 17592186044416.0 /* 2^44 */) return fail(RT_ERR_INVALID, "too many samples for the jitter jump table");
+  memset(a, 0, sizeof(*a));
+  a->width = p->width; a->height = p->height; a->S = p->samples_per_side; a->algorithm = p->algorithm;
+  a->cam.kind = p->camera.kind; a->cam.dist = p->camera.screen_distance; a->cam.aspect = p->camera.aspect_ratio;
+  memcpy(a->cam.m, p->camera.m, sizeof(a->cam.m));
+  for (int k = 0; k < 3; ++k) { a->background[k] = p->background[k]; a->onoff[k] = p->onoff_color[k]; a->ambient[k] = p->ambient[k]; }
+  a->num_of_rays = p->num_of_rays; a->max_depth = p->max_depth; a->rr_limit = p->rr_limit; a->rng_mode = p->rng_mode;
+  a->aa_state = p->aa_state; a->aa_inc = p->aa_inc; a->pt_state = p->pt_state; a->pt_inc = p->pt_inc | 1ull;
+  a->part_mode = p->part_count > 1 ? p->part_mode : RT_PART_NONE;
+  a->part_rank = p->part_rank; a->part_count = p->part_count > 1 ? p->part_count : 1;
+  a->out_f64 = p->out_f64 ? 1 : 0;
+  a->counters = s->counters;
+  build_jump_table(p->aa_inc, &a->jump);
+  return RT_OK;
+}
+
+static int ensure(void** ptr, size_t* cap, size_t bytes) {
+  if (*cap >= bytes && *ptr) return RT_OK;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr; *cap = 0;
+  CU(cudaMalloc(ptr, bytes));
+  *cap = bytes;
+  return RT_OK;
+}
+
+extern "C" int rt_render_device(rt_scene* s, const rt_render_params* p, void* d_out_rgb, int32_t* d_out_hit, void* stream) {
+  if (!s || !p || !d_out_rgb) return fail(RT_ERR_INVALID, "rt_render_device: null argument");
+  CU(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  RenderArgs a;
+  int rc = fill_args(s, p, &a);
+  if (rc != RT_OK) return rc;
+  a.out_rgb = d_out_rgb;
+  a.out_hit = d_out_hit;
+  const bool pt = p->algorithm == RT_ALGO_PATHTRACING;
+  int precision = p->precision == RT_PRECISION_AUTO ? (pt ? RT_PRECISION_F32 : RT_PRECISION_F64) : p->precision;
+  if (precision != RT_PRECISION_F32 && precision != RT_PRECISION_F64) return fail(RT_ERR_INVALID, "precision %d", p->precision);
+  int variant = p->variant;
+  if (pt) {
+    if (p->num_of_rays < 1 || p->max_depth < 0) return fail(RT_ERR_INVALID, "num_of_rays %d, max_depth %d", p->num_of_rays, p->max_depth);
+    if (variant == RT_VARIANT_AUTO) variant = (p->rng_mode == RT_RNG_REPLAY || precision == RT_PRECISION_F64) ? RT_VARIANT_MEGA : RT_VARIANT_WARP;
+    if (variant == RT_VARIANT_WARP && (p->rng_mode == RT_RNG_REPLAY || precision == RT_PRECISION_F64))
+      return fail(RT_ERR_INVALID, "the warp variant is fp32 with per-sample streams; replay / fp64 need the mega variant");
+    if (p->rng_mode == RT_RNG_REPLAY) {
+      if (!p->replay_states) return fail(RT_ERR_INVALID, "RT_RNG_REPLAY without replay_states");
+      long long S2 = p->samples_per_side > 0 ? (long long)p->samples_per_side * p->samples_per_side : 1;
+      size_t bytes = (size_t)p->width * p->height * S2 * sizeof(uint64_t);
+      if ((rc = ensure((void**)&s->replay, &s->replay_cap, bytes)) != RT_OK) return rc;
+      CU(cudaMemcpyAsync(s->replay, p->replay_states, bytes, cudaMemcpyHostToDevice, st));
+      a.replay = s->replay;
+    }
+  }
+  size_t px = (size_t)p->width * p->height;
+  CU(cudaMemsetAsync(s->counters, 0, CNT_SLOTS * sizeof(unsigned long long), st));
+  // rows this rank does not own stay zero, so that a sum over ranks is the image
+  const bool partial_rows = a.part_mode == RT_PART_ROWS;
+  long long S2 = p->samples_per_side > 0 ? (long long)p->samples_per_side * p->samples_per_side : 1;
+  const bool no_strata = a.part_mode == RT_PART_SPP && a.part_rank >= S2;
+  if (partial_rows || no_strata) {
+    CU(cudaMemsetAsync(d_out_rgb, 0, px * 3 * (a.out_f64 ? sizeof(double) : sizeof(float)), st));
+    if (d_out_hit) CU(cudaMemsetAsync(d_out_hit, 0xff, px * sizeof(int32_t), st));
+  }
+  s->last_info = {0, 0};
+  s->last_precision = precision;
+  CU(cudaEventRecord(s->ev0, st));
+  cudaError_t e = cudaSuccess;
+  const char* why = nullptr;
+  if (!pt) {
+    e = precision == RT_PRECISION_F64 ? launch_resolve<double>(view_of<double>(s), a, st, &s->last_info)
+                                      : launch_resolve<float>(view_of<float>(s), a, st, &s->last_info);
+  } else if (variant == RT_VARIANT_MEGA) {
+    e = precision == RT_PRECISION_F64 ? launch_pt_mega<double>(view_of<double>(s), a, st, &s->last_info)
+                                      : launch_pt_mega<float>(view_of<float>(s), a, st, &s->last_info);
+    if (e == cudaErrorInvalidValue) why = "max_depth > 64 with num_of_rays > 1 is not supported by the mega variant";
+  } else {
+    e = launch_pt_warp(view_of<float>(s), a, st, s->sm_count, &s->last_info, &why);
+  }
+  if (e != cudaSuccess) return fail(why ? RT_ERR_INVALID : RT_ERR_CUDA, "render launch: %s", why ? why : cudaGetErrorString(e));
+  CU(cudaEventRecord(s->ev1, st));
+  CU(cudaMemcpyAsync(s->counters_host, s->counters, CNT_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  s->pending = true;
+  return RT_OK;
+}
+
+extern "C" int rt_render_finish(rt_scene* s, void* stream, rt_stats* stats) {
+  if (!s) return fail(RT_ERR_INVALID, "rt_render_finish: null scene");
+  CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    if (s->pending) {
+      stats->rays_closest = s->counters_host[CNT_CLOSEST];
+      stats->rays_shadow = s->counters_host[CNT_SHADOW];
+      stats->samples = s->counters_host[CNT_SAMPLES];
+      stats->overflow = (int32_t)s->counters_host[CNT_OVERFLOW];
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+      stats->kernel_ms = ms;
+      stats->total_ms = ms;
+      stats->variant_used = s->last_info.variant;
+      stats->precision_used = s->last_precision;
+      stats->n_launches = s->last_info.n_launches;
+    }
+  }
+  bool ovf = s->pending && s->counters_host[CNT_OVERFLOW] != 0;
+  s->pending = false;
+  if (ovf) return fail(RT_ERR_OVERFLOW, "a warp work stack overflowed; the image is invalid");
+  return RT_OK;
+}
+
+extern "C" int rt_render(rt_scene* s, const rt_render_params* p, void* out_rgb, int32_t* out_hit, rt_stats* stats) {
+  if (!s || !p || !out_rgb) return fail(RT_ERR_INVALID, "rt_render: null argument");
+  CU(cudaSetDevice(s->device));
+  if (p->width <= 0 || p->height <= 0) return fail(RT_ERR_INVALID, "image size %dx%d", p->width, p->height);
+  size_t px = (size_t)p->width * p->height;
+  size_t bytes = px * 3 * (p->out_f64 ? sizeof(double) : sizeof(float));
+  int rc;
+  if ((rc = ensure(&s->image, &s->image_cap, bytes)) != RT_OK) return rc;
+  if (out_hit && (rc = ensure((void**)&s->hit, &s->hit_cap, px * sizeof(int32_t))) != RT_OK) return rc;
+  cudaEvent_t t0, t1;
+  CU(cudaEventCreate(&t0));
+  CU(cudaEventCreate(&t1));
+  CU(cudaEventRecord(t0, 0));
+  rc = rt_render_device(s, p, s->image, out_hit ? s->hit : nullptr, nullptr);
+  if (rc == RT_OK) {
+    cudaError_t e = cudaMemcpyAsync(out_rgb, s->image, bytes, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess && out_hit) e = cudaMemcpyAsync(out_hit, s->hit, px * sizeof(int32_t), cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaEventRecord(t1, 0);
+    if (e != cudaSuccess) rc = fail(RT_ERR_CUDA, "image copy: %s", cudaGetErrorString(e));
+  }
+  if (rc == RT_OK) rc = rt_render_finish(s, nullptr, stats);
+  if (rc == RT_OK && stats) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) stats->total_ms = ms;
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------ probes
+// Generic probe runner: packs `in` (and optional depth / pcg) into the scene's probe buffer, runs
+// k_probe in the requested precision, copies the outputs back.  Blocking; default stream.
+static int run_probe(rt_scene* s, int precision, const rt_render_params* p, int what, int n, int aux,
+                     const void* in, size_t in_bytes, const int32_t* depth, uint64_t* pcg,
+                     void* out, size_t out_bytes, int out_kind /*0 double,1 hits,2 flags,3 draws*/) {
+  if (!s) return fail(RT_ERR_INVALID, "probe: null scene");
+  CU(cudaSetDevice(s->device));
+  RenderArgs a;
+  rt_render_params dflt;
+  if (!p) {
+    memset(&dflt, 0, sizeof(dflt));
+    dflt.width = dflt.height = 1;
+    dflt.camera.kind = RT_CAMERA_PERSPECTIVE;
+    dflt.camera.screen_distance = dflt.camera.aspect_ratio = 1.0;
+    dflt.camera.m[0] = dflt.camera.m[5] = dflt.camera.m[10] = 1.0;
+    dflt.num_of_rays = 1;
+    p = &dflt;
+  }
+  int rc = fill_args(s, p, &a);
+  if (rc != RT_OK) return rc;
+  if (precision == RT_PRECISION_AUTO) precision = RT_PRECISION_F64;
+  auto align = [](size_t x) { return (x + 255) / 256 * 256; };
+  size_t off_in = 0, off_depth = align(in_bytes), off_pcg = off_depth + align(depth ? n * sizeof(int32_t) : 0);
+  size_t off_out = off_pcg + 256, total = off_out + align(out_bytes);
+  if ((rc = ensure(&s->probe_buf, &s->probe_cap, total)) != RT_OK) return rc;
+  unsigned char* base = (unsigned char*)s->probe_buf;
+  if (in_bytes) CU(cudaMemcpy(base + off_in, in, in_bytes, cudaMemcpyHostToDevice));
+  if (depth) CU(cudaMemcpy(base + off_depth, depth, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (pcg) CU(cudaMemcpy(base + off_pcg, pcg, 2 * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  CU(cudaMemset(s->counters, 0, CNT_SLOTS * sizeof(unsigned long long)));
+  ProbeArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.what = what; pa.n = n; pa.aux = aux;
+  pa.in = (const double*)(base + off_in);
+  pa.depth = depth ? (const int32_t*)(base + off_depth) : nullptr;
+  pa.pcg = (uint64_t*)(base + off_pcg);
+  pa.out = (double*)(base + off_out);
+  pa.hits = (rt_hit*)(base + off_out);
+  pa.flags = (uint8_t*)(base + off_out);
+  pa.draws = (uint32_t*)(base + off_out);
+  (void)out_kind;
+  cudaError_t e = precision == RT_PRECISION_F64 ? launch_probe<double>(view_of<double>(s), a, pa, 0)
+                                                : launch_probe<float>(view_of<float>(s), a, pa, 0);
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, "probe launch: %s", cudaGetErrorString(e));
+  CU(cudaDeviceSynchronize());
+  if (out_bytes) CU(cudaMemcpy(out, base + off_out, out_bytes, cudaMemcpyDeviceToHost));
+  if (pcg) CU(cudaMemcpy(pcg, base + off_pcg, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+extern "C" int rt_trace_rays(rt_scene* s, const rt_render_params* p, const double* rays, const int32_t* depth,
+                             int32_t n, uint64_t* pcg_state_inc, double* out_rgb) {
+  if (!p || !rays || !out_rgb || n < 0) return fail(RT_ERR_INVALID, "rt_trace_rays: bad argument");
+  if (n == 0) return RT_OK;
+  uint64_t local[2] = {p->pt_state, p->pt_inc};
+  uint64_t* pcg = pcg_state_inc ? pcg_state_inc : local;
+  int precision = p->precision == RT_PRECISION_AUTO ? RT_PRECISION_F64 : p->precision;
+  if (p->algorithm == RT_ALGO_PATHTRACING && p->num_of_rays > 1 && p->max_depth > 64)
+    return fail(RT_ERR_INVALID, "rt_trace_rays: max_depth > 64 with num_of_rays > 1");
+  return run_probe(s, precision, p, PROBE_TRACE, n, 0, rays, (size_t)n * 8 * sizeof(double), depth, pcg, out_rgb,
+                   (size_t)n * 3 * sizeof(double), 0);
+}
+
+extern "C" int rt_intersect(rt_scene* s, int32_t precision, int32_t normalize_normal, const double* rays, int32_t n, rt_hit* out) {
+  if (!rays || !out || n < 0) return fail(RT_ERR_INVALID, "rt_intersect: bad argument");
+  if (n == 0) return RT_OK;
+  return run_probe(s, precision, nullptr, PROBE_INTERSECT, n, normalize_normal ? 1 : 0, rays, (size_t)n * 8 * sizeof(double), nullptr,
+                   nullptr, out, (size_t)n * sizeof(rt_hit), 1);
+}
+
+extern "C" int rt_is_point_visible(rt_scene* s, int32_t precision, const double* pairs, int32_t n, uint8_t* out) {
+  if (!pairs || !out || n < 0) return fail(RT_ERR_INVALID, "rt_is_point_visible: bad argument");
+  if (n == 0) return RT_OK;
+  return run_probe(s, precision, nullptr, PROBE_VISIBLE, n, 0, pairs, (size_t)n * 6 * sizeof(double), nullptr, nullptr, out, (size_t)n, 2);
+}
+
+extern "C" int rt_pigment_color(rt_scene* s, int32_t pigment, int32_t precision, const double* uv, int32_t n, double* out_rgb) {
+  if (!s || !uv || !out_rgb || n < 0) return fail(RT_ERR_INVALID, "rt_pigment_color: bad argument");
+  if (pigment < 0 || pigment >= s->n_pigments) return fail(RT_ERR_INVALID, "pigment index %d out of range", pigment);
+  if (n == 0) return RT_OK;
+  return run_probe(s, precision, nullptr, PROBE_PIGMENT, n, pigment, uv, (size_t)n * 2 * sizeof(double), nullptr, nullptr, out_rgb,
+                   (size_t)n * 3 * sizeof(double), 0);
+}
+
+extern "C" int rt_scatter(rt_scene* s, int32_t material, int32_t precision, const double* in, int32_t n,
+                          uint64_t* state_inc, double* out_rays) {
+  if (!s || !in || !out_rays || !state_inc || n < 0) return fail(RT_ERR_INVALID, "rt_scatter: bad argument");
+  if (material < 0 || material >= s->n_materials) return fail(RT_ERR_INVALID, "material index %d out of range", material);
+  if (n == 0) return RT_OK;
+  return run_probe(s, precision, nullptr, PROBE_SCATTER, n, material, in, (size_t)n * 9 * sizeof(double), nullptr, state_inc,
+                   out_rays, (size_t)n * 8 * sizeof(double), 0);
+}
+
+// The scene-free probes run on a scratch empty scene.
+static int with_empty_scene(rt_scene** out) {
+  static thread_local rt_scene* empty = nullptr;
+  if (!empty) {
+    rt_scene_desc d;
+    memset(&d, 0, sizeof(d));
+    int rc = rt_scene_create(&d, &empty);
+    if (rc != RT_OK) return rc;
+  }
+  *out = empty;
+  return RT_OK;
+}
+
+extern "C" int rt_onb(int32_t precision, const double* normals, int32_t n, double* out) {
+  if (!normals || !out || n < 0) return fail(RT_ERR_INVALID, "rt_onb: bad argument");
+  rt_scene* s;
+  int rc = with_empty_scene(&s);
+  if (rc != RT_OK) return rc;
+  if (n == 0) return RT_OK;
+  return run_probe(s, precision, nullptr, PROBE_ONB, n, 0, normals, (size_t)n * 3 * sizeof(double), nullptr, nullptr, out,
+                   (size_t)n * 9 * sizeof(double), 0);
+}
+
+extern "C" int rt_pcg_draw(uint64_t* state_inc, int32_t n, uint32_t* out) {
+  if (!state_inc || !out || n < 0) return fail(RT_ERR_INVALID, "rt_pcg_draw: bad argument");
+  rt_scene* s;
+  int rc = with_empty_scene(&s);
+  if (rc != RT_OK) return rc;
+  if (n == 0) return RT_OK;
+  return run_probe(s, RT_PRECISION_F32, nullptr, PROBE_PCG_DRAW, n, 0, nullptr, 0, nullptr, state_inc, out, (size_t)n * sizeof(uint32_t), 3);
+}
+
+extern "C" int rt_pcg_seed(uint64_t init_state, uint64_t init_seq, uint64_t* state_inc) {
+  if (!state_inc) return fail(RT_ERR_INVALID, "rt_pcg_seed: bad argument");
+  rt_scene* s;
+  int rc = with_empty_scene(&s);
+  if (rc != RT_OK) return rc;
+  state_inc[0] = init_state;
+  state_inc[1] = init_seq;
+  return run_probe(s, RT_PRECISION_F32, nullptr, PROBE_PCG_SEED, 1, 0, nullptr, 0, nullptr, state_inc, nullptr, 0, 0);
+}
+
+extern "C" int rt_camera_rays(const rt_render_params* p, int32_t precision, double* out_rays) {
+  if (!p || !out_rays) return fail(RT_ERR_INVALID, "rt_camera_rays: bad argument");
+  rt_scene* s;
+  int rc = with_empty_scene(&s);
+  if (rc != RT_OK) return rc;
+  long long S2 = p->samples_per_side > 0 ? (long long)p->samples_per_side * p->samples_per_side : 1;
+  long long total = (long long)p->width * p->height * S2;
+  if (total <= 0 || total > (1ll << 28)) return fail(RT_ERR_INVALID, "rt_camera_rays: %lld rays", total);
+  return run_probe(s, precision, p, PROBE_CAMERA_RAYS, (int)total, 0, nullptr, 0, nullptr, nullptr, out_rays,
+                   (size_t)total * 8 * sizeof(double), 0);
+}
+
+extern "C" int rt_camera_fire(const rt_camera* cam, int32_t precision, const double* uv, int32_t n, double* out_rays) {
+  if (!cam || !uv || !out_rays || n < 0) return fail(RT_ERR_INVALID, "rt_camera_fire: bad argument");
+  rt_scene* s;
+  int rc = with_empty_scene(&s);
+  if (rc != RT_OK) return rc;
+  if (n == 0) return RT_OK;
+  rt_render_params p;
+  memset(&p, 0, sizeof(p));
+  p.width = p.height = 1;
+  p.camera = *cam;
+  p.num_of_rays = 1;
+  return run_probe(s, precision, &p, PROBE_CAMERA_UV, n, 0, uv, (size_t)n * 2 * sizeof(double), nullptr, nullptr, out_rays,
+                   (size_t)n * 8 * sizeof(double), 0);
+}
+
+extern "C" int rt_bench_ffma(int32_t iterations, double* tflops, float* ms_out) {
+  if (rt_device_count() <= 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
+  if (iterations < 1) iterations = 1;
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  const int blocks = prop.multiProcessorCount * 8;  // 2048 threads per SM
+  float* out = nullptr;
+  CU(cudaMalloc((void**)&out, (size_t)blocks * 256 * sizeof(float)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  cudaError_t e = launch_ffma(out, blocks, iterations, 0);  // warm-up
+  if (e == cudaSuccess) e = cudaEventRecord(e0, 0);
+  if (e == cudaSuccess) e = launch_ffma(out, blocks, iterations, 0);
+  if (e == cudaSuccess) e = cudaEventRecord(e1, 0);
+  if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+  cudaFree(out);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, "rt_bench_ffma: %s", cudaGetErrorString(e));
+  double flops = (double)blocks * 256.0 * (double)iterations * 16.0 * 8.0 * 2.0;
+  if (tflops) *tflops = flops / (ms * 1e-3) / 1e12;
+  if (ms_out) *ms_out = ms;
+  return RT_OK;
+}

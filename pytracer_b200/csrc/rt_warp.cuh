@@ -1,0 +1,323 @@
+// rt_warp.cuh — PathTracer (render.py:99-139) as a warp-cooperative wavefront (fp32).
+//
+// Why: on demo.txt 48 % of the samples trace one ray while 6.6 % trace up to 1 111; a thread-per-
+// sample walk leaves most lanes idle.  Here a warp owns a group of pixels and keeps, in shared
+// memory, a LIFO stack of *scatter records* — one per surface interaction that still owes
+// num_of_rays scattered rays {point, normal | mirror direction, child throughput, depth, rng}.
+// Every iteration the 32 lanes take the next 32 owed rays off the top of the stack (a record is
+// shared by up to N consecutive lanes: broadcast reads), each lane scatters, traces and shades its
+// ray, and the lanes whose ray must branch again push a new record; positions come from one ballot
+// (warp-level compaction).  Lanes stay full whatever single samples do, and the closest-hit loop
+// over the shapes stays perfectly convergent: all lanes walk the same shape list.
+//
+// The estimator is the reference's (N children per interaction, Russian roulette from rr_limit,
+// children cut beyond max_depth); it is linear, so each traced ray adds
+// throughput * (emitted | background) to its pixel.  Random numbers: a record carries a 64-bit
+// state; child i draws from PCG32 seeded with mix64(state + (i+1)*phi64), so the image depends only
+// on (sample index, position in the tree) and not on lane assignment, GPU count or partition.
+#pragma once
+#include "rt_kernels.cuh"
+
+#define RT_WARP_MAX_THREADS 256
+
+struct __align__(16) ScatterRec {
+  float4 a;  // P.xyz, meta (slot | kind << 5 | child depth << 8)
+  float4 b;  // nd.xyz (normal, or mirror direction for a specular surface), w.r
+  float4 c;  // w.g, w.b, rng state lo, hi
+};
+
+struct WarpCfg {
+  int cap;            // records per warp stack
+  int group;          // pixels per task (G)
+  int per_pixel;      // strata of a pixel traced by this rank (L)
+  int rounds;         // ceil(G * L / 32)
+  int per_warp_bytes;
+  int shape_bytes;    // shared memory reserved for the shape block (0 = read from global)
+  long long n_tasks;
+};
+
+RT_DEV int own_stratum(const RenderArgs& a, int ls) {
+  return (a.part_mode == RT_PART_SPP && a.part_count > 1) ? a.part_rank + ls * a.part_count : ls;
+}
+
+template <bool SHAPES_SMEM, bool MULTI_SLOT>
+__global__ void __launch_bounds__(RT_WARP_MAX_THREADS, 2)
+k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ RenderArgs a,
+          const __grid_constant__ WarpCfg cfg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* xf = sc.invm;
+  if (SHAPES_SMEM) {
+    float* sh = reinterpret_cast<float*>(smem_raw);
+    stage_shapes(sh, sc.invm, 0, sc.n_shapes);
+    __syncthreads();
+    xf = sh;
+  }
+  unsigned char* wbase = smem_raw + cfg.shape_bytes + (size_t)warp * cfg.per_warp_bytes;
+  ScatterRec* stack = reinterpret_cast<ScatterRec*>(wbase);
+  ScatterRec* cur = stack + cfg.cap;
+  float* acc = reinterpret_cast<float*>(cur + 1);  // [32][3], MULTI_SLOT only
+
+  const PixelMap pm = make_pixel_map(a);
+  const int N = a.num_of_rays;
+  const int S2 = a.S > 0 ? a.S * a.S : 1;
+  const int G = cfg.group, L = cfg.per_pixel;
+  const float inv_n = 1.0f / (float)N;
+  const float inv_spp = 1.0f / (float)S2;
+  const V3<float> background = load3<float>(a.background);
+  unsigned int n_rays = 0, n_samples = 0;
+  bool overflow = false;
+
+  while (true) {
+    long long task = 0;
+    if (lane == 0) task = (long long)atomicAdd(a.counters + CNT_TASK, 1ull);
+    task = __shfl_sync(FULL, task, 0);
+    if (task >= cfg.n_tasks) break;
+    const long long p0 = task * G;
+    float sr = 0.f, sg = 0.f, sb = 0.f;  // lane-private sums (single-slot tasks)
+    if (MULTI_SLOT) {
+      for (int i = lane; i < 96; i += 32) acc[i] = 0.f;
+      __syncwarp();
+    }
+
+    for (int round = 0; round < cfg.rounds; ++round) {
+      int top = 0, cur_rem = 0, cur_done = 0;
+      bool primary_phase = true;
+      while (true) {
+        // ---------------- pick this lane's ray
+        bool active;
+        int slot = 0, depth = 0, seg_start = lane;
+        V3<float> thr = mk3<float>(1.f, 1.f, 1.f);
+        Ray<float> ray;
+        Pcg rng;
+        long long pix = 0;
+        bool last_of_pixel = false;
+        if (primary_phase) {
+          const int j = round * 32 + lane;
+          slot = j / L;
+          const int ls = j - slot * L;
+          const long long p = p0 + slot;
+          active = (j < G * L) && (p < pm.n_pixels);
+          if (active) {
+            int col, row;
+            pm.locate(p, col, row);
+            pix = (long long)row * a.width + col;
+            const int s = own_stratum(a, ls);
+            const unsigned long long k = (unsigned long long)pix * S2 + s;
+            Pcg aa;
+            aa.inc = a.aa_inc;
+            aa.state = (a.S > 0) ? pcg_jump(a.aa_state, 2ull * k, a.jump) : 0;
+            ray = primary_ray<float>(a, col, row, s, aa);
+            rng = pcg_seed(a.pt_state, (a.pt_inc >> 1) + k);
+            last_of_pixel = (ls == L - 1);
+            ++n_samples;
+          }
+          if (MULTI_SLOT) seg_start = max(0, slot * L - round * 32);
+        } else {
+          const long long avail = (long long)cur_rem + (long long)top * N;
+          if (avail == 0) break;
+          const int take = (int)min(avail, 32ll);
+          active = lane < take;
+          const int from_cur = min(cur_rem, take);
+          ScatterRec rec;
+          int child = 0;
+          if (lane < from_cur) {
+            rec = *cur;
+            child = cur_done + lane;
+            seg_start = 0;
+          } else if (active) {
+            const int jj = lane - from_cur;
+            const int r = jj / N;
+            child = jj - r * N;
+            rec = stack[top - 1 - r];
+            seg_start = from_cur + r * N;
+          }
+          // bookkeeping, identical in all lanes
+          const int rest = take - from_cur;
+          const int full = rest / N, part = rest - full * N;
+          cur_rem -= from_cur;
+          cur_done += from_cur;
+          __syncwarp();  // every lane has read its record
+          int new_top = top - full;
+          if (part > 0) {  // the next record is only partly consumed: it becomes `cur`
+            if (lane < 3) reinterpret_cast<float4*>(cur)[lane] = reinterpret_cast<const float4*>(&stack[new_top - 1])[lane];
+            new_top -= 1;
+            cur_rem = N - part;
+            cur_done = part;
+          }
+          __syncwarp();
+          top = new_top;
+          if (active) {
+            const int meta = __float_as_int(rec.a.w);
+            slot = meta & 31;
+            depth = meta >> 8;
+            thr = mk3<float>(rec.b.w, rec.c.x, rec.c.y);
+            const uint64_t base = ((uint64_t)__float_as_uint(rec.c.w) << 32) | (uint64_t)__float_as_uint(rec.c.z);
+            rng.state = mix64(base + (uint64_t)(child + 1) * 0x9E3779B97F4A7C15ULL);
+            rng.inc = a.pt_inc;
+            ray.o = mk3<float>(rec.a.x, rec.a.y, rec.a.z);
+            ray.tmax = Num<float>::inf();
+            const V3<float> nd = mk3<float>(rec.b.x, rec.b.y, rec.b.z);
+            if (((meta >> 5) & 1) == RT_BRDF_DIFFUSE) {
+              const float u1 = pcg_random_float<float>(rng);
+              const float u2 = pcg_random_float<float>(rng);
+              ray.d = diffuse_dir<float>(nd, u1, u2);
+              ray.tmin = 1.0e-3f;
+            } else {
+              ray.d = nd;
+              ray.tmin = 1e-5f;
+            }
+          }
+        }
+
+        // ---------------- trace + shade
+        V3<float> contrib = mk3<float>(0.f, 0.f, 0.f);
+        bool push = false;
+        ScatterRec out;
+        if (active) {
+          Hit<float> h;
+          const bool found = trace_closest<float>(sc, xf, ray, h);
+          ++n_rays;
+          if (primary_phase && last_of_pixel && a.out_hit) a.out_hit[pix] = found ? sc.orig[h.idx] : -1;
+          if (!found) {
+            contrib = mul3(thr, background);
+          } else {
+            const DevMaterial& mat = sc.materials[sc.material[h.idx]];
+            V3<float> hit_color = pigment_color<float>(sc.pigments, mat.brdf_pigment, h.u, h.v);
+            const V3<float> emitted = pigment_color<float>(sc.pigments, mat.emitted_pigment, h.u, h.v);
+            contrib = mul3(thr, emitted);
+            const float lum = max3(hit_color);
+            bool go_on = true;
+            if (depth >= a.rr_limit) {  // render.py:116-123
+              const float q = fmaxf(0.05f, 1.f - lum);
+              if (pcg_random_float<float>(rng) > q) hit_color = (1.f / (1.f - q)) * hit_color;
+              else go_on = false;
+            }
+            if (go_on && lum > 0.f && depth < a.max_depth) {
+              push = true;
+              const V3<float> nd = (mat.brdf_kind == RT_BRDF_DIFFUSE) ? h.normal : specular_dir<float>(ray.d, h.normal);
+              const V3<float> w = inv_n * mul3(thr, hit_color);
+              out.a = make_float4(h.point.x, h.point.y, h.point.z,
+                                  __int_as_float(slot | (mat.brdf_kind << 5) | ((depth + 1) << 8)));
+              out.b = make_float4(nd.x, nd.y, nd.z, w.x);
+              out.c = make_float4(w.y, w.z, __uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)));
+            }
+          }
+        }
+
+        // ---------------- accumulate
+        if (MULTI_SLOT) {
+          // lanes of one record (or one pixel, for primaries) are contiguous: segmented scan
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const float r = __shfl_up_sync(FULL, contrib.x, d);
+            const float g = __shfl_up_sync(FULL, contrib.y, d);
+            const float b = __shfl_up_sync(FULL, contrib.z, d);
+            if (lane - d >= seg_start) { contrib.x += r; contrib.y += g; contrib.z += b; }
+          }
+          const int next_start = __shfl_down_sync(FULL, seg_start, 1);
+          const bool tail = (lane == 31) || (next_start != seg_start);
+          if (active && tail && (contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f)) {
+            atomicAdd(&acc[3 * slot + 0], contrib.x);
+            atomicAdd(&acc[3 * slot + 1], contrib.y);
+            atomicAdd(&acc[3 * slot + 2], contrib.z);
+          }
+        } else {
+          sr += contrib.x; sg += contrib.y; sb += contrib.z;
+        }
+
+        // ---------------- push the new records: one ballot gives every lane its slot
+        const unsigned pmask = __ballot_sync(FULL, push);
+        const int npush = __popc(pmask);
+        if (top + npush > cfg.cap) {
+          overflow = true;
+        } else if (push) {
+          stack[top + __popc(pmask & ((1u << lane) - 1u))] = out;
+        }
+        if (top + npush <= cfg.cap) top += npush;
+        __syncwarp();
+        primary_phase = false;
+      }
+    }
+
+    // ---------------- write the pixels of this task
+    if (MULTI_SLOT) {
+      __syncwarp();
+      const long long p = p0 + lane;
+      if (lane < G && p < pm.n_pixels) {
+        int col, row;
+        pm.locate(p, col, row);
+        store_pixel<float>(a, (long long)row * a.width + col,
+                           mk3<float>(acc[3 * lane] * inv_spp, acc[3 * lane + 1] * inv_spp, acc[3 * lane + 2] * inv_spp));
+      }
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        sr += __shfl_xor_sync(FULL, sr, d);
+        sg += __shfl_xor_sync(FULL, sg, d);
+        sb += __shfl_xor_sync(FULL, sb, d);
+      }
+      if (lane == 0 && p0 < pm.n_pixels) {
+        int col, row;
+        pm.locate(p0, col, row);
+        store_pixel<float>(a, (long long)row * a.width + col, mk3<float>(sr * inv_spp, sg * inv_spp, sb * inv_spp));
+      }
+    }
+  }
+  if (overflow) atomicExch(a.counters + CNT_OVERFLOW, 1ull);
+  block_count_add(a.counters + CNT_CLOSEST, n_rays);
+  block_count_add(a.counters + CNT_SAMPLES, n_samples);
+}
+
+inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderArgs& a, cudaStream_t st,
+                                       int sm_count, LaunchInfo* info, const char** why_not) {
+  PixelMap pm = make_pixel_map(a);
+  const int S2 = a.S > 0 ? a.S * a.S : 1;
+  int L = S2;
+  if (a.part_mode == RT_PART_SPP && a.part_count > 1)
+    L = a.part_rank < S2 ? (S2 - a.part_rank + a.part_count - 1) / a.part_count : 0;
+  if (pm.n_pixels == 0 || L == 0) return cudaSuccess;
+  if (a.num_of_rays < 1) { *why_not = "num_of_rays must be >= 1"; return cudaErrorInvalidValue; }
+  if (a.max_depth >= (1 << 22)) { *why_not = "max_depth too large for the warp variant"; return cudaErrorInvalidValue; }
+  WarpCfg cfg;
+  cfg.per_pixel = L;
+  cfg.group = L >= 32 ? 1 : 32 / L;
+  cfg.rounds = (cfg.group * L + 31) / 32;
+  cfg.n_tasks = (pm.n_pixels + cfg.group - 1) / cfg.group;
+  // at most ~32 records per tree level are alive at any time, one level if N == 1
+  long long cap = a.num_of_rays == 1 ? 64 : 32ll * ((long long)a.max_depth + 1);
+  if (cap < 64) cap = 64;
+  const bool multi = cfg.group > 1;
+  size_t shape_bytes = (size_t)sc.n_shapes * 48;
+  const bool shapes_smem = shape_bytes > 0 && shape_bytes <= 64 * 1024;
+  cfg.shape_bytes = shapes_smem ? (int)((shape_bytes + 15) / 16 * 16) : 0;
+  const size_t limit = 200 * 1024;
+  int warps = RT_WARP_MAX_THREADS / 32;
+  size_t per_warp = 0, smem = 0;
+  for (;; warps >>= 1) {
+    per_warp = (size_t)(cap + 1) * sizeof(ScatterRec) + (multi ? 96 * sizeof(float) : 0);
+    smem = cfg.shape_bytes + per_warp * warps;
+    if (smem <= limit || warps == 1) break;
+  }
+  if (smem > limit) { *why_not = "max_depth needs a deeper work stack than shared memory holds"; return cudaErrorInvalidValue; }
+  cfg.cap = (int)cap;
+  cfg.per_warp_bytes = (int)per_warp;
+
+  void (*kern)(const SceneView<float>, const RenderArgs, const WarpCfg);
+  if (shapes_smem) kern = multi ? k_pt_warp<true, true> : k_pt_warp<true, false>;
+  else kern = multi ? k_pt_warp<false, true> : k_pt_warp<false, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  long long blocks = (long long)per_sm * sm_count;  // persistent: every block stays resident
+  long long needed = (cfg.n_tasks + warps - 1) / warps;
+  if (blocks > needed) blocks = needed;
+  kern<<<(unsigned)blocks, warps * 32, smem, st>>>(sc, a, cfg);
+  if (info) { info->n_launches += 1; info->variant = RT_VARIANT_WARP; }
+  return cudaGetLastError();
+}

@@ -1,0 +1,372 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle and the reference's goldens.
+
+Bars (BASELINE.json north_star): deterministic renderers — hit mask / shape index bit-exact,
+colours within 1e-5 relative; path tracing — the reference image itself in replay mode (same
+random numbers, fp32 vs fp64 rounding only), and statistical agreement for the parallel streams:
+per-pixel means within 3 sigma of the Monte Carlo error and image-mean luminance within 0.5 %.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from pytracer_b200 import _abi, device, scenes
+from pytracer_b200.device import DeviceScene
+from pytracer_b200.flatten import flatten_world
+from pytracer_b200.params import make_params
+from pytracer_b200.pcg import PCG
+from util import c1_params, demo_flat, golden, luminosity, scene2_flat
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5  # colour tolerance fp32 vs Python fp64 stated by the north star
+
+
+def assert_colors_close(got, ref, rel=REL, frac_ok=1.0):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    bad = np.abs(got - ref) > rel * np.maximum(np.abs(ref), 1e-3)
+    assert bad.mean() <= 1.0 - frac_ok, f"{bad.sum()} of {bad.size} colour values differ by more than {rel} relative"
+
+
+# ------------------------------------------------------------------ PCG (tests/test_all.py:872-887)
+def test_device_pcg_known_answers():
+    state, inc = device.pcg_seed(42, 54)
+    assert (state, inc) == (1753877967969059832, 109)
+    draws, end = device.pcg_draw(state, inc, 6)
+    assert draws.tolist() == [2707161783, 2068313097, 3122475824, 2211639955, 3215226955, 3421331566]
+    ref, ref_end = oracle.pcg_draw(state, inc, 1000)
+    got, got_end = device.pcg_draw(state, inc, 1000)
+    assert np.array_equal(ref, got) and ref_end == got_end
+
+
+# ------------------------------------------------------------------ per-function known answers
+def test_closest_hit_known_answers_fp64_and_fp32():
+    fs, _, _ = scene2_flat()
+    k = golden("scene2_kat.npz")
+    sc = DeviceScene(fs)
+    hits64 = sc.intersect(k["rays"], "f64")
+    hits32 = sc.intersect(k["rays"], "f32")
+    n_mismatch32 = 0
+    for h64, h32, ref in zip(hits64, hits32, k["hits"]):
+        assert h64.shape == int(ref[0])  # bit-exact index in fp64
+        n_mismatch32 += h32.shape != int(ref[0])
+        if h64.shape >= 0:
+            got = np.array([h64.t, *h64.world_point, *h64.normal, *h64.uv])
+            assert np.allclose(got, ref[1:10], rtol=1e-12, atol=1e-12)
+            if h32.shape == h64.shape:
+                got32 = np.array([h32.t, *h32.world_point, *h32.normal])
+                assert np.allclose(got32, ref[1:8], rtol=2e-4, atol=2e-4)
+    assert n_mismatch32 <= 2  # grazing rays only
+    assert np.array_equal(sc.is_point_visible(k["pairs"], "f64"), k["visible"].astype(bool))
+    assert (sc.is_point_visible(k["pairs"], "f32") != k["visible"].astype(bool)).sum() <= 2
+
+
+def test_scatter_onb_pigments_cameras_known_answers():
+    fs, cam_p, cam_o = scene2_flat()
+    k = golden("scene2_kat.npz")
+    sc = DeviceScene(fs)
+    st, inc = 0, 0
+    st, inc = oracle.pcg_seed(17, 5)
+    for mat, tag in ((0, "diffuse"), (1, "specular")):
+        out, end = sc.scatter(mat, k["scatter_in"], st, inc, "f64")
+        assert np.allclose(out, k[f"scatter_{tag}"], rtol=1e-12, atol=1e-13)
+        assert end == int(k[f"scatter_{tag}_state_end"])
+        out32, end32 = sc.scatter(mat, k["scatter_in"], st, inc, "f32")
+        assert np.allclose(out32, k[f"scatter_{tag}"], rtol=1e-4, atol=2e-6) and end32 == end
+    assert np.allclose(device.onb(k["onb_in"], "f64"), k["onb_out"], rtol=1e-13, atol=1e-15)
+    e = device.onb(k["onb_in"], "f32").reshape(-1, 3, 3)  # tests/test_all.py:991-1011: orthonormal
+    gram = np.einsum("nij,nkj->nik", e, e)
+    assert np.allclose(gram, np.eye(3)[None], atol=1e-5)
+    mats = fs.materials
+    idx = [mats[fs.shape_material[0]].brdf_pigment, mats[fs.shape_material[3]].brdf_pigment,
+           mats[fs.shape_material[1]].brdf_pigment, mats[fs.shape_material[5]].emitted_pigment]
+    for j, pig in enumerate(idx):
+        assert np.array_equal(sc.pigment_color(pig, k["uv"], "f64"), k[f"pigment{j}"])
+        got32 = sc.pigment_color(pig, k["uv"], "f32")  # texture unit / fp32 checker cells
+        assert (np.abs(got32 - k[f"pigment{j}"]).max(axis=1) > 1e-6).mean() < 0.01
+    for cam, tag in ((cam_p, "persp"), (cam_o, "ortho")):
+        assert np.array_equal(device.camera_fire(cam, k["cam_uv"], "f64"), k[f"cam_{tag}"])
+
+
+def test_image_tracer_rays_replay_the_jitter_stream():
+    """imagetracer.py:80-101: sample k uses draws 2k, 2k+1 — the device jumps ahead, the oracle
+    draws sequentially; the rays must be identical (tests/test_all.py:556-604 restated)."""
+    _, cam_p, cam_o = scene2_flat()
+    for cam in (cam_p, cam_o):
+        for S in (0, 1, 3):
+            p = make_params(37, 23, cam, "flat", S, aa_pcg=PCG(42, 54))
+            assert np.array_equal(device.camera_rays(p, "f64"), oracle.camera_rays(p))
+
+
+def test_renderer_call_on_explicit_rays():
+    fs, cam_p, _ = scene2_flat()
+    k = golden("scene2_kat.npz")
+    sc = DeviceScene(fs)
+    bg = (0.02, 0.03, 0.04)
+    for algo in ("onoff", "flat", "pointlight"):
+        p = make_params(1, 1, cam_p, algo, background=bg, precision="f64")
+        out, _ = sc.trace_rays(p, k["call_rays"])
+        assert np.allclose(out, k[f"call_{algo}"], rtol=1e-12, atol=1e-14), algo
+    pcg = PCG(31, 41)
+    p = make_params(1, 1, cam_p, "pathtracing", num_of_rays=2, max_depth=4, rr_limit=1, background=bg, pt_pcg=pcg, precision="f64")
+    depth = np.arange(300, dtype=np.int32) % 3
+    out, (state, _) = sc.trace_rays(p, k["call_rays"], depth)
+    assert state == int(k["call_pathtracing_state_end"])  # same number of draws, same order
+    assert np.allclose(out, k["call_pathtracing"], rtol=1e-9, atol=1e-12)
+
+
+# ------------------------------------------------------------------ deterministic renderers
+@pytest.mark.parametrize("algo", ["onoff", "flat", "pointlight"])
+@pytest.mark.parametrize("s,size", [(0, (160, 120)), (2, (64, 48))])
+def test_demo_deterministic_vs_reference(algo, s, size):
+    fs, cam = demo_flat()
+    g = golden("demo_deterministic.npz")
+    sc = DeviceScene(fs)
+    p = make_params(size[0], size[1], cam, algo, s, aa_pcg=PCG(42, 54), out_f64=True)
+    rgb, hit, stats = sc.render(p, want_hit=True)
+    assert stats["precision_used"] == _abi.RT_PRECISION_F64
+    assert np.array_equal(hit, g[f"hit_s{s}"])
+    assert np.allclose(rgb, g[f"{algo}_s{s}_rgb"], rtol=1e-12, atol=1e-15)
+    assert stats["rays_closest"] == int(g[f"{algo}_s{s}_rays_closest"])
+    assert stats["rays_shadow"] == int(g[f"{algo}_s{s}_rays_shadow"])
+    # fp32 arithmetic: same image up to edge pixels
+    p32 = make_params(size[0], size[1], cam, algo, s, aa_pcg=PCG(42, 54), precision="f32")
+    rgb32, hit32, _ = sc.render(p32, want_hit=True)
+    assert (hit32 != g[f"hit_s{s}"]).mean() < 2e-3
+    assert_colors_close(rgb32, g[f"{algo}_s{s}_rgb"], rel=1e-4, frac_ok=0.995)
+
+
+@pytest.mark.parametrize("tag", ["persp", "ortho"])
+def test_scene2_deterministic_vs_reference(tag):
+    fs, cam_p, cam_o = scene2_flat()
+    cam = cam_p if tag == "persp" else cam_o
+    g = golden("scene2.npz")
+    sc = DeviceScene(fs)
+    for algo in ("onoff", "flat", "pointlight"):
+        p = make_params(96, 64, cam, algo, 0, background=(0.02, 0.03, 0.04), out_f64=True)
+        rgb, hit, stats = sc.render(p, want_hit=True)
+        assert np.array_equal(hit, g[f"{tag}_hit"]), algo
+        assert np.allclose(rgb, g[f"{tag}_{algo}_rgb"], rtol=1e-11, atol=1e-14), algo
+        assert stats["rays_shadow"] == int(g[f"{tag}_{algo}_rays_shadow"])
+
+
+def test_config2_1080p_bit_exact_hit_index_and_colours():
+    """BASELINE config 2: demo.txt, onoff + flat at 1920x1080, centre rays."""
+    fs, cam = demo_flat()
+    g = golden("demo_1080p.npz")
+    sc = DeviceScene(fs)
+    for algo in ("onoff", "flat", "pointlight"):
+        rgb, hit, stats = sc.render(make_params(1920, 1080, cam, algo, 0), want_hit=True)
+        assert np.array_equal(hit, g["hit"].astype(np.int32)), algo
+        counts = np.bincount(hit.ravel() + 1, minlength=4)
+        assert counts.tolist() == [484487, 518387, 1002874, 67852]
+        assert np.allclose(rgb.reshape(-1, 3).mean(0), g[f"{algo}_mean"], rtol=1e-6)
+        if algo != "onoff":
+            assert_colors_close(rgb, g[f"{algo}_rgb_f32"], rel=REL)
+        assert [stats["rays_closest"], stats["rays_shadow"]] == g[f"{algo}_rays"].tolist()
+
+
+# ------------------------------------------------------------------ path tracing
+def test_config1_replay_reproduces_the_reference_image():
+    """BASELINE config 1 (demo.txt 160x120, 1 spp, N=10, depth 3, seeds 42/45): feeding the device
+    the state the reference's single PCG stream has at the start of every sample reproduces the
+    reference IMAGE (not just its distribution): fp64 to rounding, fp32 within 1e-4 for all but a
+    handful of pixels where a discrete decision flips."""
+    fs, cam = demo_flat()
+    g = golden("demo_c1_pathtracing_160x120.npz")
+    states = oracle.render(fs, c1_params(cam), want_states=True)["sample_states"]
+    sc = DeviceScene(fs)
+    p = c1_params(cam, rng_mode=_abi.RT_RNG_REPLAY, variant="mega", precision="f64", out_f64=True)
+    rgb, _, stats = sc.render(p, replay_states=states)
+    assert stats["rays_closest"] == int(g["rays_closest"]) == 393440
+    assert np.allclose(rgb, g["rgb"], rtol=1e-9, atol=1e-12)
+    p = c1_params(cam, rng_mode=_abi.RT_RNG_REPLAY, variant="mega", precision="f32")
+    rgb32, _, stats32 = sc.render(p, replay_states=states)
+    assert abs(stats32["rays_closest"] - 393440) < 400
+    assert_colors_close(rgb32, g["rgb"], rel=1e-3, frac_ok=0.995)
+    assert np.allclose(rgb32.reshape(-1, 3).mean(0), g["rgb"].reshape(-1, 3).mean(0), rtol=2e-3)
+
+
+def test_replay_with_roulette_inside_the_tree():
+    fs, cam = demo_flat()
+    g = golden("demo_pt_small.npz")
+    args = dict(algorithm="pathtracing", samples_per_side=2, num_of_rays=3, max_depth=5, rr_limit=2,
+                aa_pcg=PCG(7, 11), pt_pcg=PCG(99, 3), background=(0.05, 0.02, 0.01))
+    states = oracle.render(fs, make_params(40, 30, cam, **args), want_states=True)["sample_states"]
+    sc = DeviceScene(fs)
+    p = make_params(40, 30, cam, rng_mode=_abi.RT_RNG_REPLAY, variant="mega", precision="f64", out_f64=True, **args)
+    rgb, _, stats = sc.render(p, replay_states=states)
+    assert stats["rays_closest"] == int(g["rays_closest"])
+    assert np.allclose(rgb, g["rgb"], rtol=1e-9, atol=1e-12)
+
+
+def _oracle_statistics(fs, params_fn, runs):
+    """K independent oracle renders -> per-pixel mean and standard error of the mean."""
+    imgs = []
+    for k in range(runs):
+        imgs.append(oracle.render(fs, params_fn(PCG(1000 + k, 7), PCG(2000 + k, 9)), want_hit=False)["rgb"])
+    imgs = np.stack(imgs)
+    return imgs.mean(0), imgs.std(0, ddof=1) / np.sqrt(runs)
+
+
+@pytest.mark.parametrize("variant", ["warp", "mega"])
+def test_streams_agree_statistically_with_the_reference_estimator(variant):
+    """demo.txt 160x120, N=10, depth 3: GPU at 64 spp vs 24 independent 4-spp oracle renders."""
+    fs, cam = demo_flat()
+    args = dict(algorithm="pathtracing", num_of_rays=10, max_depth=3, rr_limit=3)
+    ref_mean, ref_sem = _oracle_statistics(
+        fs, lambda aa, pt: make_params(160, 120, cam, samples_per_side=2, aa_pcg=aa, pt_pcg=pt, **args), runs=24)
+    sc = DeviceScene(fs)
+    runs = []
+    for k in range(4):
+        p = make_params(160, 120, cam, samples_per_side=4, aa_pcg=PCG(11 + k, 3), pt_pcg=PCG(77 + k, 5), variant=variant, **args)
+        rgb, _, stats = sc.render(p)
+        assert stats["variant_used"] == _abi.VARIANTS[variant] and stats["overflow"] == 0
+        runs.append(rgb.astype(np.float64))
+    runs = np.stack(runs)
+    gpu_mean, gpu_sem = runs.mean(0), runs.std(0, ddof=1) / np.sqrt(len(runs))
+    # image-mean luminance within 0.5 %
+    lum_gpu, lum_ref = luminosity(gpu_mean).mean(), luminosity(ref_mean).mean()
+    assert abs(lum_gpu - lum_ref) < 0.005 * lum_ref
+    assert abs(lum_ref - 0.29537) < 0.005 * 0.29537  # BASELINE.md anchor
+    # per-pixel means within 3 sigma of the combined Monte Carlo error
+    sigma = np.sqrt(ref_sem ** 2 + gpu_sem ** 2) + 1e-4 * np.maximum(ref_mean, 1e-3)
+    z = np.abs(gpu_mean - ref_mean) / sigma
+    assert (z < 3).mean() > 0.99, f"only {(z < 3).mean():.4f} of pixel values within 3 sigma"
+    assert np.allclose(gpu_mean.reshape(-1, 3).mean(0), ref_mean.reshape(-1, 3).mean(0), rtol=5e-3)
+    # rays per sample as the reference counts them (20.49 per sample)
+    assert abs(stats["rays_closest"] / stats["samples"] - 20.49) < 0.5
+
+
+def test_warp_and_mega_agree_on_scene2_with_deep_roulette():
+    fs, cam_p, _ = scene2_flat()
+    sc = DeviceScene(fs)
+    args = dict(algorithm="pathtracing", samples_per_side=6, num_of_rays=3, max_depth=5, rr_limit=2,
+                background=(0.02, 0.03, 0.04))
+    imgs = {}
+    for variant in ("warp", "mega"):
+        rgb, _, stats = sc.render(make_params(48, 32, cam_p, aa_pcg=PCG(3, 1), pt_pcg=PCG(4, 1), variant=variant, **args))
+        assert stats["overflow"] == 0
+        imgs[variant] = rgb.astype(np.float64)
+    ref = np.stack([oracle.render(fs, make_params(48, 32, cam_p, aa_pcg=PCG(50 + k, 1), pt_pcg=PCG(60 + k, 1), **args),
+                                  want_hit=False)["rgb"] for k in range(6)])
+    ref_mean = ref.mean(0)
+    for variant, img in imgs.items():
+        assert abs(luminosity(img).mean() - luminosity(ref_mean).mean()) < 0.01 * luminosity(ref_mean).mean(), variant
+        assert np.allclose(img.reshape(-1, 3).mean(0), ref_mean.reshape(-1, 3).mean(0), rtol=2e-2), variant
+
+
+def test_furnace():
+    """tests/test_all.py:1014-1051: inside an emissive diffuse sphere L = Le / (1 - rho)."""
+    from pytracer_b200 import Color, DiffuseBRDF, Material, Point, Ray, Sphere, UniformPigment, Vec, World
+    from pytracer_b200.render import PathTracer
+
+    a = golden("analytic.npz")
+    pcg = PCG()
+    for i in range(5):
+        emitted, refl = pcg.random_float(), pcg.random_float() * 0.9
+        assert (emitted, refl) == tuple(a["furnace"][i][:2])
+        world = World()
+        world.add_shape(Sphere(material=Material(DiffuseBRDF(UniformPigment(Color(refl, refl, refl))),
+                                                 UniformPigment(Color(emitted, emitted, emitted)))))
+        tracer = PathTracer(pcg=pcg, num_of_rays=1, world=world, max_depth=100, russian_roulette_limit=101)
+        color = tracer(Ray(origin=Point(0, 0, 0), dir=Vec(1, 0, 0)))
+        expected = emitted / (1.0 - refl)
+        assert abs(color.r - expected) < 1e-3 and abs(color.g - expected) < 1e-3 and abs(color.b - expected) < 1e-3
+        assert np.allclose(color.rgb(), a["furnace"][i][2:5], rtol=1e-9)  # the reference's own run
+        assert pcg.state == int(a[f"furnace_state1_{i}"])              # generator left where the reference leaves it
+        # warp variant: one pixel, 64 spp, same analytic answer
+        from pytracer_b200 import HdrImage, OrthogonalCamera
+        from pytracer_b200.imagetracer import CudaImageTracer
+        tracer_w = PathTracer(pcg=PCG(5, i), num_of_rays=1, world=world, max_depth=100, russian_roulette_limit=101, variant="warp")
+        img = HdrImage(2, 2)
+        cam = OrthogonalCamera(transformation=__import__("pytracer_b200").scaling(Vec(0.1, 0.1, 0.1)))
+        CudaImageTracer(img, cam, samples_per_side=3).fire_all_rays(tracer_w)
+        assert np.allclose(img.rgb_array(), expected, rtol=1e-3)
+
+
+def test_point_light_renderer_analytic():
+    """tests/test_all.py:1054-1116 restated: ambient + emitted + rho cos(45 deg) / pi."""
+    import math
+    from pytracer_b200 import (Color, DiffuseBRDF, Material, Plane, Point, PointLight, Ray, UniformPigment,
+                               Vec, World)
+    from pytracer_b200.render import PointLightRenderer
+
+    world = World()
+    world.add_shape(Plane(material=Material(DiffuseBRDF(UniformPigment(Color(0.2, 0.4, 0.6))), UniformPigment(Color(0.01, 0.02, 0.03)))))
+    world.add_light(PointLight(Point(-1.0, 0.0, 1.0), Color(1.0, 1.0, 1.0)))
+    renderer = PointLightRenderer(world=world, ambient_color=Color(0.1, 0.1, 0.1))
+    color = renderer(Ray(origin=Point(0.0, 0.0, 1.0), dir=Vec(0.0, 0.0, -1.0)))
+    cos45 = math.cos(math.pi / 4)
+    for got, rho, em in zip(color.rgb(), (0.2, 0.4, 0.6), (0.01, 0.02, 0.03)):
+        assert abs(got - (0.1 + em + rho / math.pi * cos45)) < 1e-5 * got
+
+
+def test_partitions_sum_to_the_unpartitioned_image():
+    """The multi-GPU contract: every rank's share summed over ranks is the 1-GPU image."""
+    fs, cam = demo_flat()
+    sc = DeviceScene(fs)
+    base = dict(algorithm="pathtracing", samples_per_side=4, num_of_rays=10, max_depth=3, aa_pcg=PCG(42, 54), pt_pcg=PCG(45, 54))
+    for variant in ("warp", "mega"):
+        full, _, st_full = sc.render(make_params(96, 72, cam, variant=variant, **base))
+        for count in (2, 8):
+            acc = np.zeros_like(full, dtype=np.float64)
+            rays = 0
+            for rank in range(count):
+                part, _, st = sc.render(make_params(96, 72, cam, variant=variant, part_mode=_abi.RT_PART_SPP,
+                                                    part_rank=rank, part_count=count, **base))
+                acc += part
+                rays += st["rays_closest"]
+            assert rays == st_full["rays_closest"]
+            assert np.allclose(acc, full, rtol=2e-5, atol=1e-6), (variant, count)
+    p_full = make_params(97, 61, cam, "pointlight", 2, aa_pcg=PCG(42, 54))
+    full, hit_full, _ = sc.render(p_full, want_hit=True)
+    acc = np.zeros_like(full)
+    for rank in range(3):
+        part, hit, _ = sc.render(make_params(97, 61, cam, "pointlight", 2, aa_pcg=PCG(42, 54), part_mode=_abi.RT_PART_ROWS,
+                                             part_rank=rank, part_count=3), want_hit=True)
+        acc += part
+        assert np.array_equal(hit[rank::3], hit_full[rank::3])
+    assert np.array_equal(acc, full)  # disjoint rows: x + 0 is exact
+
+
+def test_many_shapes_chunked_scan_and_textures():
+    """More shapes than one shared-memory chunk holds (fp64: 96 KB / 96 B = 1024): the chunked
+    block-synchronous sweep must pick the same winners as the oracle's plain loop."""
+    rs = scenes.random_spheres_scene(1100, 2024, 4, 20.0, with_light=True)
+    fs = flatten_world(rs.world)
+    sc = DeviceScene(fs)
+    for algo in ("flat", "pointlight"):
+        p = make_params(64, 36, rs.camera, algo, 0, out_f64=True)
+        ref = oracle.render(fs, p)
+        rgb, hit, stats = sc.render(p, want_hit=True)
+        assert np.array_equal(hit, ref["hit_index"]), algo
+        assert np.allclose(rgb, ref["rgb"], rtol=1e-9, atol=1e-12), algo
+        assert stats["rays_shadow"] == ref["rays_shadow"]
+        rgb32, hit32, _ = sc.render(make_params(64, 36, rs.camera, algo, 0, precision="f32"), want_hit=True)
+        assert (hit32 != ref["hit_index"]).mean() < 5e-3
+    # path tracing on the same scene, statistical
+    args = dict(algorithm="pathtracing", samples_per_side=2, num_of_rays=4, max_depth=2)
+    ref = np.stack([oracle.render(fs, make_params(32, 18, rs.camera, aa_pcg=PCG(k, 1), pt_pcg=PCG(k, 2), **args),
+                                  want_hit=False)["rgb"] for k in range(4)]).mean(0)
+    for variant in ("warp", "mega"):
+        rgb, _, stats = sc.render(make_params(32, 18, rs.camera, samples_per_side=4, num_of_rays=4, max_depth=2,
+                                              algorithm="pathtracing", variant=variant))
+        assert stats["overflow"] == 0
+        assert abs(luminosity(rgb).mean() - luminosity(ref).mean()) < 0.03 * luminosity(ref).mean(), variant
+
+
+def test_empty_world_and_edge_sizes():
+    from pytracer_b200 import World
+    from pytracer_b200.scene import PerspectiveCamera
+
+    sc = DeviceScene(World())
+    for algo in ("onoff", "flat", "pointlight", "pathtracing"):
+        rgb, hit, stats = sc.render(make_params(5, 3, PerspectiveCamera(), algo, 1, background=(0.25, 0.5, 0.75), num_of_rays=2, max_depth=2), want_hit=True)
+        assert np.allclose(rgb, [0.25, 0.5, 0.75]) and (hit == -1).all()
+        assert stats["rays_closest"] == 15
+    fs, cam = demo_flat()
+    sc = DeviceScene(fs)
+    rgb, hit, _ = sc.render(make_params(1, 1, cam, "flat", 0), want_hit=True)
+    assert rgb.shape == (1, 1, 3)
+    with pytest.raises(Exception):
+        sc.render(make_params(0, 4, cam, "flat", 0))

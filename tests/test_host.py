@@ -1,0 +1,151 @@
+"""CPU-side checks: host logic (flatten, PCG bookkeeping, PFM, parameter marshalling) and that the
+C-ABI library loads and exports every symbol include/rt_api.h declares.  No compute call is made."""
+import ctypes
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+
+from pytracer_b200 import _abi, _native, scenes
+from pytracer_b200.flatten import flatten_camera, flatten_world
+from pytracer_b200.hdrimage import HdrImage, read_pfm_image, InvalidPfmFileFormat
+from pytracer_b200.pcg import PCG, lcg_advance
+from pytracer_b200.scene import Color, Point, Transformation, Vec, rotation_x, rotation_y, rotation_z, scaling, translation
+from util import demo_flat, golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rt_api.h")).read()
+    declared = set(re.findall(r"\b(rt_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+    lib = _native.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.rt_api_version() == _abi.RT_API_VERSION
+
+
+def test_struct_layouts_match_the_header():
+    # sizes the C compiler gives the same structs (gcc on the header)
+    import subprocess, tempfile, textwrap
+
+    src = textwrap.dedent("""
+        #include <stdio.h>
+        #include "rt_api.h"
+        int main(void) {
+          printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(rt_pigment), sizeof(rt_material), sizeof(rt_light),
+                 sizeof(rt_scene_desc), sizeof(rt_camera), sizeof(rt_render_params), sizeof(rt_stats), sizeof(rt_hit));
+          return 0;
+        }""")
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    ours = [ctypes.sizeof(t) for t in (_abi.rt_pigment, _abi.rt_material, _abi.rt_light, _abi.rt_scene_desc,
+                                        _abi.rt_camera, _abi.rt_render_params, _abi.rt_stats, _abi.rt_hit)]
+    assert ours == sizes
+
+
+def test_no_device_means_a_loud_error_not_a_fallback():
+    lib = _native.load()
+    if lib.rt_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from pytracer_b200.device import DeviceScene
+
+    world, _ = scenes.demo_scene()
+    with pytest.raises(_native.NativeError) as err:
+        DeviceScene(world)
+    assert err.value.code == _abi.RT_ERR_NO_DEVICE
+
+
+def test_demo_scene_flattens_to_the_reference_parse():
+    """scenes.demo_scene() vs the flatten of examples/demo.txt parsed by the reference's own parser."""
+    z = golden("demo_scene.npz")
+    world, camera = scenes.demo_scene()
+    ours = flatten_world(world).to_npz_dict()
+    for key, val in ours.items():
+        assert np.array_equal(val, z[key]), key
+    cam = flatten_camera(camera)
+    assert [cam.kind, cam.screen_distance, cam.aspect_ratio] + list(cam.m) == z["camera"].tolist()
+
+
+def test_pcg_host_known_answers_and_jump_ahead():
+    pcg = PCG()  # tests/test_all.py:872-887
+    assert pcg.state == 1753877967969059832 and pcg.inc == 109
+    assert [pcg.random() for _ in range(6)] == [2707161783, 2068313097, 3122475824, 2211639955, 3215226955, 3421331566]
+    a, b = PCG(45, 54), PCG(45, 54)
+    for n in (0, 1, 2, 7, 1000, 123457):
+        start = a.state
+        for _ in range(n):
+            a.random()
+        b.advance(n)
+        assert a.state == b.state == lcg_advance(start, a.inc, n)
+
+
+def test_transformations_match_reference_known_answers():
+    # tests/test_all.py:342-472 restated
+    m = [[1.0, 2.0, 3.0, 4.0], [5.0, 6.0, 7.0, 8.0], [9.0, 9.0, 8.0, 7.0], [0.0, 0.0, 0.0, 1.0]]
+    invm = [[-3.75, 2.75, -1, 0], [5.75, -4.75, 2.0, 1.0], [-2.25, 2.25, -1.0, -2.0], [0.0, 0.0, 0.0, 1.0]]
+    t = Transformation(m, invm)
+    assert t.is_consistent()
+    assert (t * Vec(1.0, 2.0, 3.0)).is_close(Vec(14.0, 38.0, 51.0))
+    assert (t * Point(1.0, 2.0, 3.0)).is_close(Point(18.0, 46.0, 58.0))
+    from pytracer_b200.scene import Normal
+    assert (t * Normal(3.0, 2.0, 4.0)).is_close(Normal(-8.75, 7.75, -3.0))
+    assert (t * t.inverse()).is_close(Transformation())
+    for tr in (translation(Vec(1.0, 2.0, 3.0)), scaling(Vec(2.0, 5.0, 10.0)), rotation_x(0.1), rotation_y(0.1), rotation_z(0.1)):
+        assert tr.is_consistent()
+    assert (rotation_x(90) * Vec(0, 1, 0)).is_close(Vec(0, 0, 1))
+    assert (rotation_y(90) * Vec(0, 0, 1)).is_close(Vec(1, 0, 0))
+    assert (rotation_z(90) * Vec(1, 0, 0)).is_close(Vec(0, 1, 0))
+    prod = translation(Vec(1.0, 2.0, 3.0)) * translation(Vec(4.0, 6.0, 8.0))
+    assert prod.is_close(translation(Vec(5.0, 8.0, 11.0)))
+
+
+# tests/test_all.py:112-143: the reference's golden PFM bytes
+LE_REFERENCE_BYTES = bytes([
+    0x50, 0x46, 0x0a, 0x33, 0x20, 0x32, 0x0a, 0x2d, 0x31, 0x2e, 0x30, 0x0a,
+    0x00, 0x00, 0xc8, 0x42, 0x00, 0x00, 0x48, 0x43, 0x00, 0x00, 0x96, 0x43,
+    0x00, 0x00, 0xc8, 0x43, 0x00, 0x00, 0xfa, 0x43, 0x00, 0x00, 0x16, 0x44,
+    0x00, 0x00, 0x2f, 0x44, 0x00, 0x00, 0x48, 0x44, 0x00, 0x00, 0x61, 0x44,
+    0x00, 0x00, 0x20, 0x41, 0x00, 0x00, 0xa0, 0x41, 0x00, 0x00, 0xf0, 0x41,
+    0x00, 0x00, 0x20, 0x42, 0x00, 0x00, 0x48, 0x42, 0x00, 0x00, 0x70, 0x42,
+    0x00, 0x00, 0x8c, 0x42, 0x00, 0x00, 0xa0, 0x42, 0x00, 0x00, 0xb4, 0x42,
+])
+
+
+def test_pfm_write_and_read_match_the_reference_bytes():
+    img = HdrImage(3, 2)
+    vals = [[(1.0e1, 2.0e1, 3.0e1), (4.0e1, 5.0e1, 6.0e1), (7.0e1, 8.0e1, 9.0e1)],
+            [(1.0e2, 2.0e2, 3.0e2), (4.0e2, 5.0e2, 6.0e2), (7.0e2, 8.0e2, 9.0e2)]]
+    for y in range(2):
+        for x in range(3):
+            img.set_pixel(x, y, Color(*vals[y][x]))
+    buf = io.BytesIO()
+    img.write_pfm(buf)
+    assert buf.getvalue() == LE_REFERENCE_BYTES
+    back = read_pfm_image(io.BytesIO(LE_REFERENCE_BYTES))
+    assert (back.width, back.height) == (3, 2)
+    assert back.get_pixel(2, 1).is_close(Color(7.0e2, 8.0e2, 9.0e2))
+    assert back.get_pixel(0, 0).is_close(Color(1.0e1, 2.0e1, 3.0e1))
+    big = io.BytesIO()
+    img.write_pfm(big, little_endian=False)
+    assert read_pfm_image(io.BytesIO(big.getvalue())).get_pixel(1, 1).is_close(Color(4.0e2, 5.0e2, 6.0e2))
+    with pytest.raises(InvalidPfmFileFormat):
+        read_pfm_image(io.BytesIO(b"PF\n3 2\n-1.0\nstop"))
+    assert img.pixel_offset(2, 1) == 5 and img.valid_coordinates(2, 1) and not img.valid_coordinates(3, 0)
+
+
+def test_random_scene_is_reproducible_and_sized():
+    a = scenes.random_spheres_scene(64, 2024, 4, 20.0)
+    b = scenes.random_spheres_scene(64, 2024, 4, 20.0)
+    fa, fb = flatten_world(a.world), flatten_world(b.world)
+    assert fa.n_shapes == 66 and np.array_equal(fa.shape_m, fb.shape_m)
+    assert len(fa.materials) == 10 and fa.texels.shape == (512 * 256, 3)
+    text = a.to_scene_text()
+    assert text.count("sphere(") == 64 and "e-" not in text
