@@ -64,6 +64,11 @@ enum { RT_RNG_STREAMS = 0, RT_RNG_REPLAY = 1 };
  * does not own are zero), so one sum over ranks is the final image. */
 enum { RT_PART_NONE = 0, RT_PART_SPP = 1, RT_PART_ROWS = 2 };
 
+/* Content of the optional int32[H][W] side image: the shape hit by the last sample of the pixel
+ * (-1 = miss), or the number of rays (closest-hit + shadow queries) this rank traced for the
+ * pixel — the divergence map of the scene. */
+enum { RT_HIT_SHAPE = 0, RT_HIT_RAY_COUNT = 1 };
+
 enum {
   RT_OK = 0,
   RT_ERR_INVALID = -1,   /* bad argument / unsupported combination */
@@ -154,6 +159,8 @@ typedef struct rt_render_params {
   int32_t variant;
   int32_t precision;
   int32_t out_f64;          /* 1: out_rgb is double[H][W][3] instead of float */
+  int32_t hit_mode;         /* what out_hit_index receives: RT_HIT_SHAPE or RT_HIT_RAY_COUNT */
+  int32_t _pad;
 } rt_render_params;
 
 typedef struct rt_stats {

@@ -274,6 +274,7 @@ static int fill_args(const rt_scene* s, const rt_render_params* p, RenderArgs* a
   a->part_mode = p->part_count > 1 ? p->part_mode : RT_PART_NONE;
   a->part_rank = p->part_rank; a->part_count = p->part_count > 1 ? p->part_count : 1;
   a->out_f64 = p->out_f64 ? 1 : 0;
+  a->hit_mode = p->hit_mode;
   a->counters = s->counters;
   build_jump_table(p->aa_inc, &a->jump);
   return RT_OK;

@@ -204,7 +204,7 @@ k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
   if (active) {
     if (a.S > 0) cum = ((T)1 / (T)(S2)) * cum;  // imagetracer.py:99-101
     store_pixel<T>(a, pix, cum);
-    if (a.out_hit) a.out_hit[pix] = last_hit;
+    if (a.out_hit) a.out_hit[pix] = a.hit_mode == RT_HIT_RAY_COUNT ? (int)(n_closest + n_shadow) : last_hit;
   }
   block_count_add(a.counters + CNT_CLOSEST, n_closest);
   block_count_add(a.counters + CNT_SHADOW, n_shadow);
@@ -361,7 +361,7 @@ k_pt_mega(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
     }
     if (a.S > 0) cum = ((T)1 / (T)(S2)) * cum;
     store_pixel<T>(a, pix, cum);
-    if (a.out_hit) a.out_hit[pix] = last_hit;
+    if (a.out_hit) a.out_hit[pix] = a.hit_mode == RT_HIT_RAY_COUNT ? (int)cx.n_rays : last_hit;
   }
   block_count_add(a.counters + CNT_CLOSEST, cx.n_rays);
   block_count_add(a.counters + CNT_SAMPLES, n_samples);

@@ -14,6 +14,7 @@ struct RenderArgs {
   uint64_t aa_state, aa_inc, pt_state, pt_inc;
   const uint64_t* replay;  // device copy of rt_render_params.replay_states
   int32_t part_mode, part_rank, part_count, out_f64;
+  int32_t hit_mode, _pad;
   void* out_rgb;           // float or double [H][W][3]
   int32_t* out_hit;        // optional
   unsigned long long* counters;

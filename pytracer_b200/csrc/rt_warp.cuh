@@ -58,6 +58,8 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
   ScatterRec* stack = reinterpret_cast<ScatterRec*>(wbase);
   ScatterRec* cur = stack + cfg.cap;
   float* acc = reinterpret_cast<float*>(cur + 1);  // [32][3], MULTI_SLOT only
+  int* slot_rays = reinterpret_cast<int*>(acc + 96);  // [32], MULTI_SLOT + RT_HIT_RAY_COUNT only
+  const bool count_rays = a.out_hit != nullptr && a.hit_mode == RT_HIT_RAY_COUNT;
 
   const PixelMap pm = make_pixel_map(a);
   const int N = a.num_of_rays;
@@ -76,8 +78,10 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
     if (task >= cfg.n_tasks) break;
     const long long p0 = task * G;
     float sr = 0.f, sg = 0.f, sb = 0.f;  // lane-private sums (single-slot tasks)
+    unsigned int task_rays = 0;
     if (MULTI_SLOT) {
       for (int i = lane; i < 96; i += 32) acc[i] = 0.f;
+      slot_rays[lane] = 0;
       __syncwarp();
     }
 
@@ -179,7 +183,12 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
           Hit<float> h;
           const bool found = trace_closest<float>(sc, xf, ray, h);
           ++n_rays;
-          if (primary_phase && last_of_pixel && a.out_hit) a.out_hit[pix] = found ? sc.orig[h.idx] : -1;
+          if (count_rays) {
+            if (MULTI_SLOT) atomicAdd(&slot_rays[slot], 1);
+            else ++task_rays;
+          } else if (primary_phase && last_of_pixel && a.out_hit) {
+            a.out_hit[pix] = found ? sc.orig[h.idx] : -1;
+          }
           if (!found) {
             contrib = mul3(thr, background);
           } else {
@@ -250,6 +259,7 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
         pm.locate(p, col, row);
         store_pixel<float>(a, (long long)row * a.width + col,
                            mk3<float>(acc[3 * lane] * inv_spp, acc[3 * lane + 1] * inv_spp, acc[3 * lane + 2] * inv_spp));
+        if (count_rays) a.out_hit[(long long)row * a.width + col] = slot_rays[lane];
       }
       __syncwarp();
     } else {
@@ -259,10 +269,12 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
         sg += __shfl_xor_sync(FULL, sg, d);
         sb += __shfl_xor_sync(FULL, sb, d);
       }
+      task_rays = __reduce_add_sync(FULL, task_rays);
       if (lane == 0 && p0 < pm.n_pixels) {
         int col, row;
         pm.locate(p0, col, row);
         store_pixel<float>(a, (long long)row * a.width + col, mk3<float>(sr * inv_spp, sg * inv_spp, sb * inv_spp));
+        if (count_rays) a.out_hit[(long long)row * a.width + col] = (int)task_rays;
       }
     }
   }
@@ -297,7 +309,7 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   int warps = RT_WARP_MAX_THREADS / 32;
   size_t per_warp = 0, smem = 0;
   for (;; warps >>= 1) {
-    per_warp = (size_t)(cap + 1) * sizeof(ScatterRec) + (multi ? 96 * sizeof(float) : 0);
+    per_warp = (size_t)(cap + 1) * sizeof(ScatterRec) + (multi ? 96 * sizeof(float) + 32 * sizeof(int) : 0);
     smem = cfg.shape_bytes + per_warp * warps;
     if (smem <= limit || warps == 1) break;
   }

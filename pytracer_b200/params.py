@@ -37,6 +37,7 @@ def make_params(
     variant="auto",
     precision="auto",
     out_f64: bool = False,
+    hit_mode: int = _abi.RT_HIT_SHAPE,
 ) -> _abi.rt_render_params:
     p = _abi.rt_render_params()
     p.width, p.height, p.samples_per_side = int(width), int(height), int(samples_per_side)
@@ -56,4 +57,5 @@ def make_params(
     p.variant = _abi.VARIANTS[variant] if isinstance(variant, str) else int(variant)
     p.precision = _abi.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
     p.out_f64 = 1 if out_f64 else 0
+    p.hit_mode = hit_mode
     return p
