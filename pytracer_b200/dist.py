@@ -78,17 +78,26 @@ class TorchComm:
         dist.barrier(group=self.group)
 
 
-def render_partitioned(scene, params: _abi.rt_render_params, comm) -> Tuple[np.ndarray, dict]:
-    """This rank's share on its GPU, one NCCL all-reduce of the fp32 image, image to the host."""
+def _render_share_cuda(scene, p: _abi.rt_render_params):
+    """This rank's share, rendered into a device tensor on torch's current stream."""
     import torch
 
-    p = partition_params(params, comm.rank, comm.world_size)
     image = torch.empty((p.height, p.width, 3), dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     scene.render_device(p, image.data_ptr(), 0, stream)
-    stats = scene.finish(stream)
+    return image, scene.finish(stream)
+
+
+def render_partitioned(scene, params: _abi.rt_render_params, comm, render_share=_render_share_cuda) -> Tuple[np.ndarray, dict]:
+    """This rank's share on its GPU, ONE all-reduce(sum) of the fp32 image, image to the host.
+    ``render_share(scene, partitioned_params) -> (tensor, stats)`` is injectable so that the exchange
+    logic can be exercised on CPU (gloo) with the oracle standing in for the GPU."""
+    import torch
+
+    p = partition_params(params, comm.rank, comm.world_size)
+    image, stats = render_share(scene, p)
     comm.all_reduce_sum(image)
-    counts = torch.tensor([stats["rays_closest"], stats["rays_shadow"], stats["samples"]], dtype=torch.int64, device="cuda")
+    counts = torch.tensor([stats["rays_closest"], stats["rays_shadow"], stats["samples"]], dtype=torch.int64, device=image.device)
     comm.all_reduce_sum(counts)
     stats = dict(stats)
     stats["rays_closest"], stats["rays_shadow"], stats["samples"] = (int(v) for v in counts.tolist())

@@ -149,3 +149,58 @@ def test_random_scene_is_reproducible_and_sized():
     assert len(fa.materials) == 10 and fa.texels.shape == (512 * 256, 3)
     text = a.to_scene_text()
     assert text.count("sphere(") == 64 and "e-" not in text
+
+
+def test_builtin_scene_reader_matches_the_reference_parse(tmp_path, monkeypatch):
+    """pytracer_b200.scene_text on the text of examples/demo.txt (restated here) == the flatten of the
+    scene parsed by the reference's parser (tests/golden/demo_scene.npz)."""
+    from pytracer_b200.scene_text import GrammarError, parse_scene_text
+
+    text = '''
+    float clock(150)
+    material sky_material(diffuse(uniform(<0, 0, 0>)), uniform(<0.7, 0.5, 1>))
+    # a comment
+    material ground_material(diffuse(checkered(<0.3, 0.5, 0.1>, <0.1, 0.2, 0.5>, 4)), uniform(<0, 0, 0>))
+    material sphere_material(specular(uniform(<0.5, 0.5, 0.5>)), uniform(<0, 0, 0>))
+    point_light([10, 10, 10], <1, 1, 1>, 1)
+    plane (sky_material, translation([0, 0, 100]) * rotation_y(clock))
+    plane (ground_material, identity)
+    sphere(sphere_material, translation([0, 0, 1]))
+    camera(perspective, rotation_z(30) * translation([-4, 0, 1]), 1.0, 1.0)
+    '''
+    z = golden("demo_scene.npz")
+    sc = parse_scene_text(text)
+    ours = flatten_world(sc.world).to_npz_dict()
+    for key, val in ours.items():
+        assert np.array_equal(val, z[key]), key
+    cam = flatten_camera(sc.camera)
+    assert [cam.kind, cam.screen_distance, cam.aspect_ratio] + list(cam.m) == z["camera"].tolist()
+    # -d NAME:VALUE overrides win over the file's own definition (scene_file.py:654-675)
+    sc2 = parse_scene_text(text, {"clock": 10.0})
+    assert sc2.float_variables["clock"] == 10.0
+    assert not np.array_equal(flatten_world(sc2.world).shape_m, ours["shape_m"])
+    # the reference's two error cases (tests/test_all.py:1309-1332)
+    with pytest.raises(GrammarError):
+        parse_scene_text("plane(this_material_does_not_exist, identity)")
+    with pytest.raises(GrammarError):
+        parse_scene_text("camera(perspective, rotation_z(30) * translation([-4, 0, 1]), 1.0, 1.0)\n"
+                         "camera(orthogonal, identity, 1.0, 1.0)")
+    # generated scenes round-trip through their text form
+    rs = scenes.random_spheres_scene(12, 2024, 4, 20.0)
+    monkeypatch.chdir(tmp_path)
+    with open("texture.pfm", "wb") as f:
+        rs.texture.write_pfm(f)
+    back = flatten_world(parse_scene_text(rs.to_scene_text()).world).to_npz_dict()
+    for key, val in flatten_world(rs.world).to_npz_dict().items():
+        assert np.array_equal(val, back[key]), key
+
+
+def test_tone_mapping_matches_reference_known_answers():
+    # tests/test_all.py:239-268 restated on the vectorised host implementation
+    from pytracer_b200.tonemap import average_luminosity, tone_map
+
+    img = np.array([[[5.0, 10.0, 15.0], [500.0, 1000.0, 1500.0]]])
+    assert abs(average_luminosity(img, delta=0.0) - 100.0) < 1e-9
+    out = tone_map(img, factor=1000.0, luminosity=100.0)
+    assert np.allclose(out[0, 0] / (1 - out[0, 0]), [0.5e2, 1.0e2, 1.5e2])
+    assert (out >= 0).all() and (out <= 1).all()
