@@ -31,6 +31,7 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+SCALE = 1
 METRIC = "path-traced rays/sec (demo.txt 1080p)"
 UNIT = "rays/s"
 
@@ -60,6 +61,9 @@ def workload(name):
         raise SystemExit(f"unknown workload {name}")
     # 54 per sphere test, 12 per plane test, 60 for the winner's record, 46 scatter
     flops_per_ray = 54 * n_sph + 12 * n_pl + 60 + 46
+    if SCALE > 1:
+        kw["width"], kw["height"] = kw["width"] // SCALE, kw["height"] // SCALE
+        desc += f" [SCALED DOWN {SCALE}x per side: experiment, not the benchmark]"
     return world, camera, kw, desc, flops_per_ray
 
 
@@ -308,7 +312,11 @@ def main():
     ap.add_argument("--variant", default="auto", choices=["auto", "mega", "warp"])
     ap.add_argument("--precision", default="auto", choices=["auto", "f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scale", type=int, default=1, help="divide width and height by this (quick experiments only; "
+                    "a scaled run is NOT the benchmark and says so in config)")
     args = ap.parse_args()
+    global SCALE
+    SCALE = max(1, args.scale)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))

@@ -12,4 +12,4 @@ nvcc $ARCH $COMMON --fmad=false -c rt_kernels_f64.cu -o build/rt_kernels_f64.o &
 nvcc $ARCH $COMMON -c rt_api.cu -o build/rt_api.o &
 wait
 nvcc $ARCH -shared -o $OUT build/rt_kernels_f32.o build/rt_kernels_f64.o build/rt_api.o -lcudart_static -lpthread -ldl -lrt
-echo "built $(realpath $OUT)"
+[ -f $OUT ] && echo "built $(realpath $OUT)"

@@ -225,7 +225,9 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
       return fail(RT_ERR_INVALID, "material %d: bad BRDF kind or pigment index", i);
     }
     mats[i].brdf_kind = m.brdf_kind; mats[i].brdf_pigment = m.brdf_pigment; mats[i].emitted_pigment = m.emitted_pigment;
-    mats[i]._pad = 0; mats[i].threshold = m.threshold_angle_rad;
+    mats[i].uses_uv = (d->pigments[m.brdf_pigment].kind != RT_PIGMENT_UNIFORM) ||
+                      (d->pigments[m.emitted_pigment].kind != RT_PIGMENT_UNIFORM);
+    mats[i].threshold = m.threshold_angle_rad;
   }
   UP(materials, mats)
   std::vector<DevLight> lights(d->n_lights);

@@ -22,7 +22,8 @@ struct DevPigment {
   double c1d[3], c2d[3];
 };
 struct DevMaterial {
-  int32_t brdf_kind, brdf_pigment, emitted_pigment, _pad;
+  int32_t brdf_kind, brdf_pigment, emitted_pigment;
+  int32_t uses_uv;  // 0 when both pigments are uniform: the hit record can skip atan2 / acos
   double threshold;
 };
 struct DevLight {
@@ -81,6 +82,25 @@ template <typename T> RT_DEV T plane_t(const T* im, const Ray<T>& r) {
   return t;
 }
 
+// world.py:62 keeps the FIRST shape of World.shapes on equal t; spheres are scanned before planes
+// here, so a plane that ties with the current best sphere wins iff it came first in World.shapes.
+// Out of line: ties are rare and the two global loads must not be hoisted into the scan loop.
+static __device__ __noinline__ bool plane_wins_tie(const int32_t* __restrict__ orig, int plane, int best) {
+  return orig[plane] < orig[best];
+}
+
+template <typename T>
+RT_DEV void scan_planes(const T* __restrict__ xf, int begin, int end, int n_spheres,
+                        const int32_t* __restrict__ orig, const Ray<T>& r, T& best_t, int& best) {
+  for (int i = max(begin, n_spheres); i < end; ++i) {
+    T t = plane_t(xf + 12 * (i - begin), r);
+    if (t < best_t) { best_t = t; best = i; }
+    else if (t == best_t && best >= 0 && best < n_spheres) {
+      if (plane_wins_tie(orig, i, best)) { best_t = t; best = i; }
+    }
+  }
+}
+
 // Closest-hit scan over sorted shapes [begin, end) held at `xf` (xf[0] is shape `begin`); the data
 // may live in shared or global memory.  All lanes walk the same shapes: loads are broadcasts.
 // Start with best_t = +inf, best = -1.
@@ -93,12 +113,7 @@ RT_DEV void scan_closest(const T* __restrict__ xf, int begin, int end, int n_sph
     T t = sphere_t(xf + 12 * (i - begin), r);
     if (t < best_t) { best_t = t; best = i; }
   }
-  for (int i = max(begin, n_spheres); i < end; ++i) {
-    T t = plane_t(xf + 12 * (i - begin), r);
-    bool take = t < best_t;
-    if (!take && t == best_t && best >= 0) take = orig[i] < orig[best];
-    if (take) { best_t = t; best = i; }
-  }
+  scan_planes<T>(xf, begin, end, n_spheres, orig, r, best_t, best);
 }
 
 // shapes.py:133-151 / :191-198 — true as soon as one shape blocks the segment
@@ -131,9 +146,131 @@ RT_DEV bool scan_any(const T* __restrict__ xf, int begin, int end, int n_spheres
   return false;
 }
 
+// ---------------------------------------------------------------- fp32 production scans
+// Same mathematics as sphere_t<float> (shapes.py:97-121), arranged for the FMA pipe: the ray is
+// taken to the sphere's frame with 18 FFMA, a, b/2 and c cost 9 more, delta/4 = (b/2)^2 - a c two:
+// 29 FMA-pipe instructions and three broadcast LDS.128 per sphere, nothing else in the common case.
+// Spheres are tested four at a time; the few whose line is crossed (delta > 0) go to a per-lane
+// candidate list and only those get the sqrt / reciprocal / range tests after the sweep — so the
+// sweep itself has one (rarely taken) branch per four spheres.
+RT_DEV float sphere_qdelta(const float* __restrict__ im, const Ray<float>& r, float& a, float& hb) {
+  const float4 r0 = reinterpret_cast<const float4*>(im)[0];
+  const float4 r1 = reinterpret_cast<const float4*>(im)[1];
+  const float4 r2 = reinterpret_cast<const float4*>(im)[2];
+  const float px = fmaf(r0.x, r.o.x, fmaf(r0.y, r.o.y, fmaf(r0.z, r.o.z, r0.w)));
+  const float py = fmaf(r1.x, r.o.x, fmaf(r1.y, r.o.y, fmaf(r1.z, r.o.z, r1.w)));
+  const float pz = fmaf(r2.x, r.o.x, fmaf(r2.y, r.o.y, fmaf(r2.z, r.o.z, r2.w)));
+  const float dx = fmaf(r0.x, r.d.x, fmaf(r0.y, r.d.y, r0.z * r.d.z));
+  const float dy = fmaf(r1.x, r.d.x, fmaf(r1.y, r.d.y, r1.z * r.d.z));
+  const float dz = fmaf(r2.x, r.d.x, fmaf(r2.y, r.d.y, r2.z * r.d.z));
+  a = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+  hb = fmaf(px, dx, fmaf(py, dy, pz * dz));
+  const float c = fmaf(px, px, fmaf(py, py, fmaf(pz, pz, -1.0f)));
+  return fmaf(hb, hb, -a * c);
+}
+
+// roots of the crossed sphere: t = (-b/2 -+ sqrt(delta/4)) / a, first one inside (tmin, tmax)
+RT_DEV float sphere_root(float a, float hb, float qd, float tmin, float tmax) {
+  const float sd = fast_sqrt(qd), inv = fast_rcp(a);
+  const float t1 = (-hb - sd) * inv, t2 = (-hb + sd) * inv;
+  if (t1 > tmin && t1 < tmax) return t1;
+  if (t2 > tmin && t2 < tmax) return t2;
+  return Num<float>::inf();
+}
+
+#define RT_CAND_CAP 16
+
+// Sweeps spheres [i0, i1) (data at xf, xf[0] = sphere `base`); returns the number of crossed spheres,
+// the first RT_CAND_CAP of them in cand[] in ascending order.
+RT_DEV int sweep_spheres(const float* __restrict__ xf, int base, int i0, int i1, const Ray<float>& r, int* cand) {
+  int nc = 0;
+  int i = i0;
+  for (; i + 4 <= i1; i += 4) {
+    float a, hb;
+    const float* q = xf + 12 * (i - base);
+    const float d0 = sphere_qdelta(q, r, a, hb);
+    const float d1 = sphere_qdelta(q + 12, r, a, hb);
+    const float d2 = sphere_qdelta(q + 24, r, a, hb);
+    const float d3 = sphere_qdelta(q + 36, r, a, hb);
+    if (fmaxf(fmaxf(d0, d1), fmaxf(d2, d3)) > 0.0f) {
+      if (d0 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = i; ++nc; }
+      if (d1 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = i + 1; ++nc; }
+      if (d2 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = i + 2; ++nc; }
+      if (d3 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = i + 3; ++nc; }
+    }
+  }
+  for (; i < i1; ++i) {
+    float a, hb;
+    if (sphere_qdelta(xf + 12 * (i - base), r, a, hb) > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = i; ++nc; }
+  }
+  return nc;
+}
+
+template <>
+RT_DEV void scan_closest<float>(const float* __restrict__ xf, int begin, int end, int n_spheres,
+                                const int32_t* __restrict__ orig, const Ray<float>& r, float& best_t, int& best) {
+  const int s_end = min(end, n_spheres);
+  if (begin < s_end) {
+    int cand[RT_CAND_CAP];
+    const int nc = sweep_spheres(xf, begin, begin, s_end, r, cand);
+    if (nc <= RT_CAND_CAP) {
+      for (int j = 0; j < nc; ++j) {  // ascending index: strict '<' keeps the first shape on ties
+        const int i = cand[j];
+        float a, hb;
+        const float qd = sphere_qdelta(xf + 12 * (i - begin), r, a, hb);
+        const float t = sphere_root(a, hb, qd, r.tmin, r.tmax);
+        if (t < best_t) { best_t = t; best = i; }
+      }
+    } else {  // a line through more than RT_CAND_CAP spheres: plain pass
+      for (int i = begin; i < s_end; ++i) {
+        float a, hb;
+        const float qd = sphere_qdelta(xf + 12 * (i - begin), r, a, hb);
+        if (qd > 0.0f) {
+          const float t = sphere_root(a, hb, qd, r.tmin, r.tmax);
+          if (t < best_t) { best_t = t; best = i; }
+        }
+      }
+    }
+  }
+  scan_planes<float>(xf, begin, end, n_spheres, orig, r, best_t, best);
+}
+
+template <>
+RT_DEV bool scan_any<float>(const float* __restrict__ xf, int begin, int end, int n_spheres, const Ray<float>& r) {
+  const int s_end = min(end, n_spheres);
+  // planes first: a handful of shapes that often decide the query (ground, sky)
+  for (int i = max(begin, n_spheres); i < end; ++i)
+    if (plane_t<float>(xf + 12 * (i - begin), r) < Num<float>::inf()) return true;
+  if (begin < s_end) {
+    int cand[RT_CAND_CAP];
+    const int nc = sweep_spheres(xf, begin, begin, s_end, r, cand);
+    if (nc <= RT_CAND_CAP) {
+      for (int j = 0; j < nc; ++j) {
+        float a, hb;
+        const float qd = sphere_qdelta(xf + 12 * (cand[j] - begin), r, a, hb);
+        const float sd = fast_sqrt(qd), inv = fast_rcp(a);
+        const float t1 = (-hb - sd) * inv, t2 = (-hb + sd) * inv;
+        if ((r.tmin < t1 && t1 < r.tmax) || (r.tmin < t2 && t2 < r.tmax)) return true;
+      }
+    } else {
+      for (int i = begin; i < s_end; ++i) {
+        float a, hb;
+        const float qd = sphere_qdelta(xf + 12 * (i - begin), r, a, hb);
+        if (qd > 0.0f) {
+          const float sd = fast_sqrt(qd), inv = fast_rcp(a);
+          const float t1 = (-hb - sd) * inv, t2 = (-hb + sd) * inv;
+          if ((r.tmin < t1 && t1 < r.tmax) || (r.tmin < t2 && t2 < r.tmax)) return true;
+        }
+      }
+    }
+  }
+  return false;
+}
+
 // Hit record of the winning shape (shapes.py:123-131 / :176-189) + world.py:66-67
 template <typename T>
-RT_DEV void finish_hit(const SceneView<T>& sc, const Ray<T>& r, T t, int idx, Hit<T>& h, bool normalise = true) {
+RT_DEV void finish_hit(const SceneView<T>& sc, const Ray<T>& r, T t, int idx, Hit<T>& h, bool normalise = true,
+                       bool force_uv = false) {
   const T* im = sc.invm + 12 * (size_t)idx;
   const T* mm = sc.m + 12 * (size_t)idx;
   V3<T> o = xf_point(im, r.o);
@@ -143,12 +280,15 @@ RT_DEV void finish_hit(const SceneView<T>& sc, const Ray<T>& r, T t, int idx, Hi
   h.t = t;
   h.point = xf_point(mm, hp);
   V3<T> n;
+  h.u = h.v = (T)0;
   if (idx < sc.n_spheres) {
     n = (dot(hp, d) < (T)0) ? hp : -hp;  // shapes.py:45-54
-    T u = Num<T>::atan2(hp.y, hp.x) / (T)(2.0 * 3.14159265358979323846);  // shapes.py:36-42
-    h.u = (u >= (T)0) ? u : u + (T)1;
-    T z = Num<T>::min((T)1, Num<T>::max((T)-1, hp.z));  // the reference would raise outside [-1,1]
-    h.v = Num<T>::acos(z) / (T)3.14159265358979323846;
+    if (force_uv || sc.materials[sc.material[idx]].uses_uv) {
+      T u = Num<T>::atan2(hp.y, hp.x) / (T)(2.0 * 3.14159265358979323846);  // shapes.py:36-42
+      h.u = (u >= (T)0) ? u : u + (T)1;
+      T z = Num<T>::min((T)1, Num<T>::max((T)-1, hp.z));  // the reference would raise outside [-1,1]
+      h.v = Num<T>::acos(z) / (T)3.14159265358979323846;
+    }
   } else {
     n = mk3<T>((T)0, (T)0, (d.z < (T)0) ? (T)1 : (T)-1);
     h.u = hp.x - Num<T>::floor(hp.x);
@@ -175,8 +315,13 @@ template <> RT_DEV V3<float> pig_c2<float>(const DevPigment& p) { return mk3<flo
 template <> RT_DEV V3<double> pig_c2<double>(const DevPigment& p) { return mk3<double>(p.c2d[0], p.c2d[1], p.c2d[2]); }
 
 template <typename T> RT_DEV V3<T> pig_texel(const DevPigment& p, int col, int row);
+// out of line: image pigments are the rare case and the fetch must not be if-converted into the
+// uniform / checkered paths
+static __device__ __noinline__ float4 fetch_texel(cudaTextureObject_t tex, float x, float y) {
+  return tex2D<float4>(tex, x, y);  // texture unit, nearest texel
+}
 template <> RT_DEV V3<float> pig_texel<float>(const DevPigment& p, int col, int row) {
-  float4 t = tex2D<float4>(p.tex, col + 0.5f, row + 0.5f);  // texture unit, nearest texel
+  float4 t = fetch_texel(p.tex, col + 0.5f, row + 0.5f);
   return mk3<float>(t.x, t.y, t.z);
 }
 template <> RT_DEV V3<double> pig_texel<double>(const DevPigment& p, int col, int row) {

@@ -457,7 +457,7 @@ __global__ void k_probe(const __grid_constant__ SceneView<T> sc, const __grid_co
       scan_closest<T>(sc.invm, 0, sc.n_shapes, sc.n_spheres, sc.orig, r, best_t, best);
       if (best < 0) { out.shape = -1; out.material = -1; }
       else {
-        finish_hit<T>(sc, r, best_t, best, h, p.aux != 0);
+        finish_hit<T>(sc, r, best_t, best, h, p.aux != 0, true);
         out.shape = sc.orig[best]; out.material = sc.material[best]; out.t = h.t;
         out.world_point[0] = h.point.x; out.world_point[1] = h.point.y; out.world_point[2] = h.point.z;
         out.normal[0] = h.normal.x; out.normal[1] = h.normal.y; out.normal[2] = h.normal.z;

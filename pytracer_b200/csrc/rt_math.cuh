@@ -13,11 +13,23 @@
 
 template <typename T> struct Num;
 
+// single-instruction MUFU forms (approx, flush-to-zero): 1-2 ulp, no slow-path call, no range fix-up
+RT_DEV float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+RT_DEV float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 template <> struct Num<float> {
   static constexpr bool is_f64 = false;
-  static RT_DEV float sqrt(float x) { return sqrtf(x); }
+  static RT_DEV float sqrt(float x) { return fast_sqrt(x); }
   static RT_DEV float rsqrt(float x) { return rsqrtf(x); }
-  static RT_DEV float div(float a, float b) { return __fdividef(a, b); }
+  static RT_DEV float div(float a, float b) { return a * fast_rcp(b); }
   static RT_DEV float floor(float x) { return floorf(x); }
   static RT_DEV float abs(float x) { return fabsf(x); }
   static RT_DEV float max(float a, float b) { return fmaxf(a, b); }
@@ -32,7 +44,7 @@ template <> struct Num<float> {
     *c = -__cosf(x);
   }
   static RT_DEV float inf() { return __int_as_float(0x7f800000); }
-  static RT_DEV long long floor_ll(float x) { return (long long)floorf(x); }
+  static RT_DEV long long floor_ll(float x) { return (long long)__float2int_rd(x); }  // parity only
 };
 
 template <> struct Num<double> {

@@ -65,6 +65,9 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
   const int N = a.num_of_rays;
   const int S2 = a.S > 0 ? a.S * a.S : 1;
   const int G = cfg.group, L = cfg.per_pixel;
+  // x / N for 0 <= x <= 32 as a multiply-shift (exact for N <= 1024; beyond that x / N is 0 or 1)
+  const unsigned n_magic = N <= 1024 ? (65536u + (unsigned)N - 1u) / (unsigned)N : 0u;
+  auto div_n = [&](int x) -> int { return n_magic ? (int)(((unsigned)x * n_magic) >> 16) : (x >= N ? 1 : 0); };
   const float inv_n = 1.0f / (float)N;
   const float inv_spp = 1.0f / (float)S2;
   const V3<float> background = load3<float>(a.background);
@@ -132,14 +135,14 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
             seg_start = 0;
           } else if (active) {
             const int jj = lane - from_cur;
-            const int r = jj / N;
+            const int r = div_n(jj);
             child = jj - r * N;
             rec = stack[top - 1 - r];
             seg_start = from_cur + r * N;
           }
           // bookkeeping, identical in all lanes
           const int rest = take - from_cur;
-          const int full = rest / N, part = rest - full * N;
+          const int full = div_n(rest), part = rest - full * N;
           cur_rem -= from_cur;
           cur_done += from_cur;
           __syncwarp();  // every lane has read its record

@@ -373,3 +373,43 @@ def test_empty_world_and_edge_sizes():
     assert rgb.shape == (1, 1, 3)
     with pytest.raises(Exception):
         sc.render(make_params(0, 4, cam, "flat", 0))
+
+
+DEMO_TEXT = '''
+float clock(150)
+material sky_material(diffuse(uniform(<0, 0, 0>)), uniform(<0.7, 0.5, 1>))
+material ground_material(diffuse(checkered(<0.3, 0.5, 0.1>, <0.1, 0.2, 0.5>, 4)), uniform(<0, 0, 0>))
+material sphere_material(specular(uniform(<0.5, 0.5, 0.5>)), uniform(<0, 0, 0>))
+point_light([10, 10, 10], <1, 1, 1>, 1)
+plane (sky_material, translation([0, 0, 100]) * rotation_y(clock))
+plane (ground_material, identity)
+sphere(sphere_material, translation([0, 0, 1]))
+camera(perspective, rotation_z(30) * translation([-4, 0, 1]), 1.0, 1.0)
+'''
+
+
+def test_render_command_writes_the_reference_image(tmp_path):
+    """`render --algorithm flat` (the reference's CLI options, main.py:76-129) -> PFM == golden."""
+    from click.testing import CliRunner
+
+    from pytracer_b200.hdrimage import read_pfm_image
+    from pytracer_b200.main import cli
+
+    scene_file = tmp_path / "demo.txt"
+    scene_file.write_text(DEMO_TEXT)
+    pfm, png = tmp_path / "out.pfm", tmp_path / "out.png"
+    res = CliRunner().invoke(cli, ["render", "--width", "160", "--height", "120", "--algorithm", "flat",
+                                   "--samples-per-pixel", "0", "--pfm-output", str(pfm), "--png-output", str(png),
+                                   "--parser", "builtin", str(scene_file)])
+    assert res.exit_code == 0, res.output
+    assert "Using flat renderer" in res.output
+    with open(pfm, "rb") as f:
+        img = read_pfm_image(f)
+    g = golden("demo_deterministic.npz")
+    assert np.array_equal(img.rgb_array(), g["flat_s0_rgb"].astype(np.float32))
+    assert png.exists() and png.stat().st_size > 100
+    res = CliRunner().invoke(cli, ["render", "--samples-per-pixel", "3", str(scene_file)])
+    assert "must be a perfect square" in res.output
+    res = CliRunner().invoke(cli, ["render", "--width", "64", "--height", "48", "--samples-per-pixel", "4",
+                                   "--pfm-output", str(pfm), "--png-output", str(png), str(scene_file)])
+    assert res.exit_code == 0 and "Using a path tracer" in res.output
