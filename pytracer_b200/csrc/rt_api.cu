@@ -35,7 +35,8 @@ static int fail(int code, const char* fmt, ...) {
 struct rt_scene {
   int device = 0, sm_count = 0;
   int n_shapes = 0, n_spheres = 0, n_materials = 0, n_pigments = 0, n_lights = 0;
-  float *invm32 = nullptr, *m32 = nullptr;
+  float *invm32 = nullptr, *m32 = nullptr, *packed32 = nullptr;
+  int n_pairs = 0;
   double *invm64 = nullptr, *m64 = nullptr;
   int32_t *orig = nullptr, *material = nullptr;
   DevMaterial* materials = nullptr;
@@ -85,6 +86,7 @@ template <> SceneView<float> view_of<float>(const rt_scene* s) {
   v.invm = s->invm32; v.m = s->m32; v.orig = s->orig; v.material = s->material;
   v.materials = s->materials; v.pigments = s->pigments; v.lights = s->lights;
   v.n_shapes = s->n_shapes; v.n_spheres = s->n_spheres; v.n_lights = s->n_lights;
+  v.packed = s->packed32; v.n_pairs = s->n_pairs; v._pad = 0;
   return v;
 }
 template <> SceneView<double> view_of<double>(const rt_scene* s) {
@@ -92,6 +94,7 @@ template <> SceneView<double> view_of<double>(const rt_scene* s) {
   v.invm = s->invm64; v.m = s->m64; v.orig = s->orig; v.material = s->material;
   v.materials = s->materials; v.pigments = s->pigments; v.lights = s->lights;
   v.n_shapes = s->n_shapes; v.n_spheres = s->n_spheres; v.n_lights = s->n_lights;
+  v.packed = nullptr; v.n_pairs = 0; v._pad = 0;
   return v;
 }
 
@@ -107,7 +110,7 @@ extern "C" void rt_scene_destroy(rt_scene* s) {
   cudaSetDevice(s->device);
   for (auto t : s->textures) cudaDestroyTextureObject(t);
   for (auto a : s->arrays) cudaFreeArray(a);
-  cudaFree(s->invm32); cudaFree(s->m32); cudaFree(s->invm64); cudaFree(s->m64);
+  cudaFree(s->invm32); cudaFree(s->m32); cudaFree(s->packed32); cudaFree(s->invm64); cudaFree(s->m64);
   cudaFree(s->orig); cudaFree(s->material); cudaFree(s->materials); cudaFree(s->pigments);
   cudaFree(s->lights); cudaFree(s->texels64); cudaFree(s->counters); cudaFree(s->replay);
   cudaFree(s->image); cudaFree(s->hit); cudaFree(s->probe_buf);
@@ -156,6 +159,15 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
   int rc;
 #define UP(field, vec) if ((rc = upload(&s->field, vec)) != RT_OK) { rt_scene_destroy(s); return rc; }
   UP(invm32, invm32) UP(m32, m32) UP(invm64, invm64) UP(m64, m64) UP(orig, orig) UP(material, mat)
+  // fp32 scan array: sphere pairs element-interleaved (operands of the packed FFMA2 sweep), odd count
+  // padded with an all-zero record (never crossed), then the plane records
+  s->n_pairs = (s->n_spheres + 1) / 2;
+  std::vector<float> packed((size_t)s->n_pairs * 24 + (size_t)(s->n_shapes - s->n_spheres) * 12, 0.0f);
+  for (int i = 0; i < s->n_spheres; ++i)
+    for (int k = 0; k < 12; ++k) packed[(size_t)(i / 2) * 24 + 2 * k + (i & 1)] = invm32[12 * (size_t)i + k];
+  for (int i = s->n_spheres; i < s->n_shapes; ++i)
+    for (int k = 0; k < 12; ++k) packed[(size_t)s->n_pairs * 24 + 12 * (size_t)(i - s->n_spheres) + k] = invm32[12 * (size_t)i + k];
+  UP(packed32, packed)
 
   // ---- textures: fp64 copy for the fp64 path, float4 CUDA arrays behind texture objects for fp32
   std::vector<double> tex64;

@@ -43,6 +43,9 @@ template <typename T> struct SceneView {
   const DevPigment* pigments;
   const DevLight* lights;
   int32_t n_shapes, n_spheres, n_lights;
+  // fp32 only: [n_pairs][24] element-interleaved sphere pairs followed by [n_planes][12] planes
+  const float* packed;
+  int32_t n_pairs, _pad;
 };
 
 template <typename T> struct Hit {
@@ -166,7 +169,7 @@ RT_DEV float sphere_qdelta(const float* __restrict__ im, const Ray<float>& r, fl
   a = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
   hb = fmaf(px, dx, fmaf(py, dy, pz * dz));
   const float c = fmaf(px, px, fmaf(py, py, fmaf(pz, pz, -1.0f)));
-  return fmaf(hb, hb, -a * c);
+  return __fsub_rn(__fmul_rn(hb, hb), __fmul_rn(a, c));  // unfused: bit-identical to the packed sweep
 }
 
 // roots of the crossed sphere: t = (-b/2 -+ sqrt(delta/4)) / a, first one inside (tmin, tmax)
@@ -180,91 +183,190 @@ RT_DEV float sphere_root(float a, float hb, float qd, float tmin, float tmax) {
 
 #define RT_CAND_CAP 16
 
-// Sweeps spheres [i0, i1) (data at xf, xf[0] = sphere `base`); returns the number of crossed spheres,
-// the first RT_CAND_CAP of them in cand[] in ascending order.
-RT_DEV int sweep_spheres(const float* __restrict__ xf, int base, int i0, int i1, const Ray<float>& r, int* cand) {
-  int nc = 0;
-  int i = i0;
-  for (; i + 4 <= i1; i += 4) {
-    float a, hb;
-    const float* q = xf + 12 * (i - base);
-    const float d0 = sphere_qdelta(q, r, a, hb);
-    const float d1 = sphere_qdelta(q + 12, r, a, hb);
-    const float d2 = sphere_qdelta(q + 24, r, a, hb);
-    const float d3 = sphere_qdelta(q + 36, r, a, hb);
-    if (fmaxf(fmaxf(d0, d1), fmaxf(d2, d3)) > 0.0f) {
-      if (d0 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = i; ++nc; }
-      if (d1 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = i + 1; ++nc; }
-      if (d2 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = i + 2; ++nc; }
-      if (d3 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = i + 3; ++nc; }
-    }
-  }
-  for (; i < i1; ++i) {
-    float a, hb;
-    if (sphere_qdelta(xf + 12 * (i - base), r, a, hb) > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = i; ++nc; }
-  }
-  return nc;
+// ---- packed sweep: two spheres per FFMA2 (Blackwell fma.rn.f32x2) -------------------------------
+// The fp32 scan array stores spheres in PAIRS, element-interleaved: pair p holds, for each of the 12
+// matrix entries, {entry of sphere 2p, entry of sphere 2p+1} — 24 floats = six LDS.128, each register
+// pair of which is directly a packed operand.  The ray components enter as scalar broadcast operands
+// (FFMA2 Rd, Ra.F32x2, Rb.F32, Rc.F32x2), so one sphere pair costs 30 packed FMA-pipe instructions
+// instead of 58 scalar ones: issue slots per sphere drop from ~36 to ~19 and the register-bank
+// pressure of three-source FFMAs disappears (a 64-bit operand always takes one word from each bank).
+// An odd sphere count is padded with an all-zero record (a = 0, c = -1: delta = 0, never crossed).
+typedef unsigned long long f32x2;
+RT_DEV f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+RT_DEV void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+RT_DEV f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+RT_DEV f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+RT_DEV f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+struct PackedRay {  // ray components as broadcast pairs (the compiler turns them into .F32 scalar operands)
+  f32x2 ox, oy, oz, dx, dy, dz;
+};
+RT_DEV PackedRay pack_ray(const Ray<float>& r) {
+  PackedRay q;
+  q.ox = pk2(r.o.x, r.o.x); q.oy = pk2(r.o.y, r.o.y); q.oz = pk2(r.o.z, r.o.z);
+  q.dx = pk2(r.d.x, r.d.x); q.dy = pk2(r.d.y, r.d.y); q.dz = pk2(r.d.z, r.d.z);
+  return q;
 }
 
-template <>
-RT_DEV void scan_closest<float>(const float* __restrict__ xf, int begin, int end, int n_spheres,
-                                const int32_t* __restrict__ orig, const Ray<float>& r, float& best_t, int& best) {
-  const int s_end = min(end, n_spheres);
-  if (begin < s_end) {
-    int cand[RT_CAND_CAP];
-    const int nc = sweep_spheres(xf, begin, begin, s_end, r, cand);
-    if (nc <= RT_CAND_CAP) {
-      for (int j = 0; j < nc; ++j) {  // ascending index: strict '<' keeps the first shape on ties
-        const int i = cand[j];
-        float a, hb;
-        const float qd = sphere_qdelta(xf + 12 * (i - begin), r, a, hb);
+// delta/4 of both spheres of one pair (24 floats at `q`)
+RT_DEV f32x2 pair_qdelta(const float4* __restrict__ q, const PackedRay& r) {
+  const float4 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3], v4 = q[4], v5 = q[5];
+  const f32x2 m00 = pk2(v0.x, v0.y), m01 = pk2(v0.z, v0.w), m02 = pk2(v1.x, v1.y), m03 = pk2(v1.z, v1.w);
+  const f32x2 m10 = pk2(v2.x, v2.y), m11 = pk2(v2.z, v2.w), m12 = pk2(v3.x, v3.y), m13 = pk2(v3.z, v3.w);
+  const f32x2 m20 = pk2(v4.x, v4.y), m21 = pk2(v4.z, v4.w), m22 = pk2(v5.x, v5.y), m23 = pk2(v5.z, v5.w);
+  const f32x2 px = fma2(m00, r.ox, fma2(m01, r.oy, fma2(m02, r.oz, m03)));
+  const f32x2 py = fma2(m10, r.ox, fma2(m11, r.oy, fma2(m12, r.oz, m13)));
+  const f32x2 pz = fma2(m20, r.ox, fma2(m21, r.oy, fma2(m22, r.oz, m23)));
+  const f32x2 dx = fma2(m00, r.dx, fma2(m01, r.dy, mul2(m02, r.dz)));
+  const f32x2 dy = fma2(m10, r.dx, fma2(m11, r.dy, mul2(m12, r.dz)));
+  const f32x2 dz = fma2(m20, r.dx, fma2(m21, r.dy, mul2(m22, r.dz)));
+  const f32x2 a = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));
+  const f32x2 hb = fma2(px, dx, fma2(py, dy, mul2(pz, dz)));
+  const f32x2 c = fma2(px, px, fma2(py, py, fma2(pz, pz, pk2(-1.0f, -1.0f))));
+  return sub2(mul2(hb, hb), mul2(a, c));
+}
+
+// Sweeps sphere pairs [p0, p1) whose data starts at `pairs` (pairs[0] = pair `base`); crossed spheres
+// are appended to cand[] (ring of RT_CAND_CAP; nc counts all of them) as sorted sphere indices.
+RT_DEV void sweep_pairs(const float4* __restrict__ pairs, int base, int p0, int p1, const PackedRay& r,
+                        int* cand, int& nc) {
+  int p = p0;
+  for (; p + 2 <= p1; p += 2) {
+    const float4* q = pairs + 6 * (p - base);
+    float a0, a1, b0, b1;
+    upk2(pair_qdelta(q, r), a0, a1);
+    upk2(pair_qdelta(q + 6, r), b0, b1);
+    if (fmaxf(fmaxf(a0, a1), fmaxf(b0, b1)) > 0.0f) {
+      if (a0 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = 2 * p; ++nc; }
+      if (a1 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = 2 * p + 1; ++nc; }
+      if (b0 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = 2 * p + 2; ++nc; }
+      if (b1 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = 2 * p + 3; ++nc; }
+    }
+  }
+  if (p < p1) {
+    float a0, a1;
+    upk2(pair_qdelta(pairs + 6 * (p - base), r), a0, a1);
+    if (a0 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = 2 * p; ++nc; }
+    if (a1 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = 2 * p + 1; ++nc; }
+  }
+}
+
+// Exact roots for the crossed spheres only, from the plain [n][12] array in global memory (a few per
+// ray: L1/L2 hits).  Ascending index + strict '<' keeps the first shape on ties (world.py:62).
+RT_DEV void resolve_candidates(const float* __restrict__ invm, int n_spheres, const int* cand, int nc,
+                               const Ray<float>& r, float& best_t, int& best) {
+  if (nc <= RT_CAND_CAP) {
+    for (int j = 0; j < nc; ++j) {
+      const int i = cand[j];
+      float a, hb;
+      const float qd = sphere_qdelta(invm + 12 * (size_t)i, r, a, hb);
+      if (qd > 0.0f) {
         const float t = sphere_root(a, hb, qd, r.tmin, r.tmax);
         if (t < best_t) { best_t = t; best = i; }
       }
-    } else {  // a line through more than RT_CAND_CAP spheres: plain pass
-      for (int i = begin; i < s_end; ++i) {
-        float a, hb;
-        const float qd = sphere_qdelta(xf + 12 * (i - begin), r, a, hb);
-        if (qd > 0.0f) {
-          const float t = sphere_root(a, hb, qd, r.tmin, r.tmax);
-          if (t < best_t) { best_t = t; best = i; }
-        }
+    }
+  } else {  // a line through more than RT_CAND_CAP spheres: plain pass
+    for (int i = 0; i < n_spheres; ++i) {
+      float a, hb;
+      const float qd = sphere_qdelta(invm + 12 * (size_t)i, r, a, hb);
+      if (qd > 0.0f) {
+        const float t = sphere_root(a, hb, qd, r.tmin, r.tmax);
+        if (t < best_t) { best_t = t; best = i; }
       }
     }
   }
-  scan_planes<float>(xf, begin, end, n_spheres, orig, r, best_t, best);
 }
 
-template <>
-RT_DEV bool scan_any<float>(const float* __restrict__ xf, int begin, int end, int n_spheres, const Ray<float>& r) {
-  const int s_end = min(end, n_spheres);
-  // planes first: a handful of shapes that often decide the query (ground, sky)
-  for (int i = max(begin, n_spheres); i < end; ++i)
-    if (plane_t<float>(xf + 12 * (i - begin), r) < Num<float>::inf()) return true;
-  if (begin < s_end) {
-    int cand[RT_CAND_CAP];
-    const int nc = sweep_spheres(xf, begin, begin, s_end, r, cand);
-    if (nc <= RT_CAND_CAP) {
-      for (int j = 0; j < nc; ++j) {
-        float a, hb;
-        const float qd = sphere_qdelta(xf + 12 * (cand[j] - begin), r, a, hb);
-        const float sd = fast_sqrt(qd), inv = fast_rcp(a);
-        const float t1 = (-hb - sd) * inv, t2 = (-hb + sd) * inv;
-        if ((r.tmin < t1 && t1 < r.tmax) || (r.tmin < t2 && t2 < r.tmax)) return true;
-      }
-    } else {
-      for (int i = begin; i < s_end; ++i) {
-        float a, hb;
-        const float qd = sphere_qdelta(xf + 12 * (i - begin), r, a, hb);
-        if (qd > 0.0f) {
-          const float sd = fast_sqrt(qd), inv = fast_rcp(a);
-          const float t1 = (-hb - sd) * inv, t2 = (-hb + sd) * inv;
-          if ((r.tmin < t1 && t1 < r.tmax) || (r.tmin < t2 && t2 < r.tmax)) return true;
-        }
-      }
+RT_DEV bool sphere_blocks(const float* __restrict__ im, const Ray<float>& r) {
+  float a, hb;
+  const float qd = sphere_qdelta(im, r, a, hb);
+  if (!(qd > 0.0f)) return false;
+  const float sd = fast_sqrt(qd), inv = fast_rcp(a);
+  const float t1 = (-hb - sd) * inv, t2 = (-hb + sd) * inv;
+  return (r.tmin < t1 && t1 < r.tmax) || (r.tmin < t2 && t2 < r.tmax);
+}
+
+RT_DEV bool any_candidate_blocks(const float* __restrict__ invm, int n_spheres, const int* cand, int nc,
+                                 const Ray<float>& r) {
+  if (nc <= RT_CAND_CAP) {
+    for (int j = 0; j < nc; ++j)
+      if (sphere_blocks(invm + 12 * (size_t)cand[j], r)) return true;
+    return false;
+  }
+  for (int i = 0; i < n_spheres; ++i)
+    if (sphere_blocks(invm + 12 * (size_t)i, r)) return true;
+  return false;
+}
+
+// planes [0, n_planes) at `planes` (12 floats each; sorted index = n_spheres + k)
+RT_DEV void scan_plane_block(const float* __restrict__ planes, int n_spheres, int n_planes,
+                             const int32_t* __restrict__ orig, const Ray<float>& r, float& best_t, int& best) {
+  for (int k = 0; k < n_planes; ++k) {
+    const float t = plane_t<float>(planes + 12 * k, r);
+    const int i = n_spheres + k;
+    if (t < best_t) { best_t = t; best = i; }
+    else if (t == best_t && best >= 0 && best < n_spheres) {
+      if (plane_wins_tie(orig, i, best)) { best_t = t; best = i; }
     }
   }
+}
+RT_DEV bool any_plane_blocks(const float* __restrict__ planes, int n_planes, const Ray<float>& r) {
+  for (int k = 0; k < n_planes; ++k)
+    if (plane_t<float>(planes + 12 * k, r) < Num<float>::inf()) return true;
   return false;
+}
+
+// ---- where a kernel reads the scan data from (shared memory copy or global memory) ----------------
+template <typename T> struct ScanSrc {  // generic: [n][12] inverse transforms
+  const T* xf;
+};
+template <> struct ScanSrc<float> {     // fp32: packed pairs + plane records
+  const float4* pairs;
+  const float* planes;
+};
+
+template <typename T> RT_DEV ScanSrc<T> global_src(const SceneView<T>& sc) {
+  ScanSrc<T> s;
+  s.xf = sc.invm;
+  return s;
+}
+template <> RT_DEV ScanSrc<float> global_src<float>(const SceneView<float>& sc) {
+  ScanSrc<float> s;
+  s.pairs = reinterpret_cast<const float4*>(sc.packed);
+  s.planes = sc.packed + 24 * (size_t)sc.n_pairs;
+  return s;
+}
+
+// World.ray_intersection's loop over ALL shapes (world.py:55-64): index of the winner, -1 = miss
+template <typename T>
+RT_DEV void closest_all(const SceneView<T>& sc, const ScanSrc<T>& src, const Ray<T>& r, T& best_t, int& best) {
+  scan_closest<T>(src.xf, 0, sc.n_shapes, sc.n_spheres, sc.orig, r, best_t, best);
+}
+template <>
+RT_DEV void closest_all<float>(const SceneView<float>& sc, const ScanSrc<float>& src, const Ray<float>& r,
+                               float& best_t, int& best) {
+  if (sc.n_pairs > 0) {
+    int cand[RT_CAND_CAP];
+    int nc = 0;
+    const PackedRay pr = pack_ray(r);
+    sweep_pairs(src.pairs, 0, 0, sc.n_pairs, pr, cand, nc);
+    resolve_candidates(sc.invm, sc.n_spheres, cand, nc, r, best_t, best);
+  }
+  scan_plane_block(src.planes, sc.n_spheres, sc.n_shapes - sc.n_spheres, sc.orig, r, best_t, best);
+}
+
+// World.is_point_visible's loop (world.py:76-78): does any shape block the segment?
+template <typename T> RT_DEV bool any_all(const SceneView<T>& sc, const ScanSrc<T>& src, const Ray<T>& r) {
+  return scan_any<T>(src.xf, 0, sc.n_shapes, sc.n_spheres, r);
+}
+template <> RT_DEV bool any_all<float>(const SceneView<float>& sc, const ScanSrc<float>& src, const Ray<float>& r) {
+  if (any_plane_blocks(src.planes, sc.n_shapes - sc.n_spheres, r)) return true;
+  if (sc.n_pairs == 0) return false;
+  int cand[RT_CAND_CAP];
+  int nc = 0;
+  const PackedRay pr = pack_ray(r);
+  sweep_pairs(src.pairs, 0, 0, sc.n_pairs, pr, cand, nc);
+  return any_candidate_blocks(sc.invm, sc.n_spheres, cand, nc, r);
 }
 
 // Hit record of the winning shape (shapes.py:123-131 / :176-189) + world.py:66-67

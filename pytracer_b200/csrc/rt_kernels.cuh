@@ -60,13 +60,18 @@ RT_DEV void block_count_add(unsigned long long* counter, unsigned int v) {
   if ((threadIdx.x & 31) == 0 && v) atomicAdd(counter, (unsigned long long)v);
 }
 
-// cooperative copy of shapes [c0, c1) (12 T each) from global to shared memory, 16 B per thread
-template <typename T> RT_DEV void stage_shapes(T* sh, const T* g, int c0, int c1) {
-  const uint4* src = reinterpret_cast<const uint4*>(g + 12 * (size_t)c0);
+// cooperative copy global -> shared memory, 16 B per thread (both sides 16-byte aligned)
+RT_DEV void stage_bytes(void* sh, const void* g, size_t bytes) {
+  const uint4* src = reinterpret_cast<const uint4*>(g);
   uint4* dst = reinterpret_cast<uint4*>(sh);
-  int n16 = (c1 - c0) * 12 * (int)sizeof(T) / 16;
+  const int n16 = (int)(bytes / 16);
   for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
 }
+// shapes [c0, c1) of a [n][12] array
+template <typename T> RT_DEV void stage_shapes(T* sh, const T* g, int c0, int c1) {
+  stage_bytes(sh, g + 12 * (size_t)c0, (size_t)(c1 - c0) * 12 * sizeof(T));
+}
+#define RT_PLANES_SMEM_MAX 341  // plane records kept in shared memory next to the sphere chunk (16 KB)
 
 // primary ray of sample (col,row,stratum) — fp64 generation, rounded to T
 template <typename T>
@@ -119,13 +124,25 @@ RT_DEV V3<T> light_term(const SceneView<T>& sc, const Hit<T>& h, V3<T> ray_dir, 
 }
 
 // ---------------------------------------------------------------- k_resolve
+// `chunk` = shapes (fp64) or sphere PAIRS (fp32) staged per sweep step; everything in one chunk when
+// it fits.  fp32 keeps the plane records in a small resident block and sweeps packed sphere pairs;
+// crossed spheres are collected over all chunks and resolved once from global memory.
 template <typename T>
 __global__ void __launch_bounds__(RT_RESOLVE_THREADS)
 k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ RenderArgs a, const int chunk) {
+  constexpr bool F32 = sizeof(T) == 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = sc.n_shapes, n_planes = sc.n_shapes - sc.n_spheres;
+  const int n_units = F32 ? sc.n_pairs : n;
+  const bool single = n_units <= chunk;
+  // fp32 layout: [plane records (if few)][pair chunk]; fp64 layout: [shape chunk]
+  const bool planes_smem = F32 && n_planes <= RT_PLANES_SMEM_MAX;
+  const float* planes_g = F32 ? reinterpret_cast<const float*>(sc.packed) + 24 * (size_t)sc.n_pairs : nullptr;
+  float* sh_planes = reinterpret_cast<float*>(smem_raw);
+  float4* sh_pairs = reinterpret_cast<float4*>(smem_raw + (planes_smem ? (size_t)n_planes * 48 : 0));
   T* sh = reinterpret_cast<T*>(smem_raw);
-  const int n = sc.n_shapes;
-  const bool single = n <= chunk;
+  const float* planes = planes_smem ? sh_planes : planes_g;
+
   const PixelMap pm = make_pixel_map(a);
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = p < pm.n_pixels;
@@ -134,7 +151,11 @@ k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
   const long long pix = (long long)row * a.width + col;
   const int S2 = a.S > 0 ? a.S * a.S : 1;
 
-  if (single) {
+  if (F32) {
+    if (planes_smem) stage_bytes(sh_planes, planes_g, (size_t)n_planes * 48);
+    if (single) stage_bytes(sh_pairs, sc.packed, (size_t)sc.n_pairs * 96);
+    __syncthreads();
+  } else if (single) {
     stage_shapes(sh, sc.invm, 0, n);
     __syncthreads();
   }
@@ -154,15 +175,37 @@ k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
     // ---- closest hit: all threads of the block sweep the shape chunks together
     T best_t = Num<T>::inf();
     int best = -1;
-    if (single) {
-      if (mine) scan_closest<T>(sh, 0, n, sc.n_spheres, sc.orig, ray, best_t, best);
+    if constexpr (F32) {
+      int cand[RT_CAND_CAP];
+      int nc = 0;
+      PackedRay pr;
+      if (mine) pr = pack_ray(ray);
+      if (single) {
+        if (mine) sweep_pairs(sh_pairs, 0, 0, sc.n_pairs, pr, cand, nc);
+      } else {
+        for (int c0 = 0; c0 < sc.n_pairs; c0 += chunk) {
+          const int c1 = min(c0 + chunk, sc.n_pairs);
+          __syncthreads();
+          stage_bytes(sh_pairs, sc.packed + 24 * (size_t)c0, (size_t)(c1 - c0) * 96);
+          __syncthreads();
+          if (mine) sweep_pairs(sh_pairs, c0, c0, c1, pr, cand, nc);
+        }
+      }
+      if (mine) {
+        resolve_candidates(sc.invm, sc.n_spheres, cand, nc, ray, best_t, best);
+        scan_plane_block(planes, sc.n_spheres, n_planes, sc.orig, ray, best_t, best);
+      }
     } else {
-      for (int c0 = 0; c0 < n; c0 += chunk) {
-        int c1 = min(c0 + chunk, n);
-        __syncthreads();
-        stage_shapes(sh, sc.invm, c0, c1);
-        __syncthreads();
-        if (mine) scan_closest<T>(sh, c0, c1, sc.n_spheres, sc.orig, ray, best_t, best);
+      if (single) {
+        if (mine) scan_closest<T>(sh, 0, n, sc.n_spheres, sc.orig, ray, best_t, best);
+      } else {
+        for (int c0 = 0; c0 < n; c0 += chunk) {
+          int c1 = min(c0 + chunk, n);
+          __syncthreads();
+          stage_shapes(sh, sc.invm, c0, c1);
+          __syncthreads();
+          if (mine) scan_closest<T>(sh, c0, c1, sc.n_spheres, sc.orig, ray, best_t, best);
+        }
       }
     }
     if (mine) { ++n_closest; ++n_samples; }
@@ -185,15 +228,34 @@ k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
         Ray<T> sr;
         if (need) { sr = shadow_ray<T>(load3<T>(sc.lights[l].pos), h.point); ++n_shadow; }
         bool blocked = false;
-        if (single) {
-          if (need) blocked = scan_any<T>(sh, 0, n, sc.n_spheres, sr);
-        } else if (__syncthreads_or(need)) {
-          for (int c0 = 0; c0 < n; c0 += chunk) {
-            int c1 = min(c0 + chunk, n);
-            __syncthreads();
-            stage_shapes(sh, sc.invm, c0, c1);
-            __syncthreads();
-            if (need && !blocked) blocked = scan_any<T>(sh, c0, c1, sc.n_spheres, sr);
+        if constexpr (F32) {
+          int cand[RT_CAND_CAP];
+          int nc = 0;
+          PackedRay pr;
+          if (need) { pr = pack_ray(sr); blocked = any_plane_blocks(planes, n_planes, sr); }
+          if (single) {
+            if (need && !blocked) sweep_pairs(sh_pairs, 0, 0, sc.n_pairs, pr, cand, nc);
+          } else if (__syncthreads_or(need && !blocked)) {
+            for (int c0 = 0; c0 < sc.n_pairs; c0 += chunk) {
+              const int c1 = min(c0 + chunk, sc.n_pairs);
+              __syncthreads();
+              stage_bytes(sh_pairs, sc.packed + 24 * (size_t)c0, (size_t)(c1 - c0) * 96);
+              __syncthreads();
+              if (need && !blocked) sweep_pairs(sh_pairs, c0, c0, c1, pr, cand, nc);
+            }
+          }
+          if (need && !blocked) blocked = any_candidate_blocks(sc.invm, sc.n_spheres, cand, nc, sr);
+        } else {
+          if (single) {
+            if (need) blocked = scan_any<T>(sh, 0, n, sc.n_spheres, sr);
+          } else if (__syncthreads_or(need)) {
+            for (int c0 = 0; c0 < n; c0 += chunk) {
+              int c1 = min(c0 + chunk, n);
+              __syncthreads();
+              stage_shapes(sh, sc.invm, c0, c1);
+              __syncthreads();
+              if (need && !blocked) blocked = scan_any<T>(sh, c0, c1, sc.n_spheres, sr);
+            }
           }
         }
         if (need && !blocked) color = color + light_term<T>(sc, h, ray.d, l);
@@ -215,12 +277,16 @@ template <typename T>
 cudaError_t launch_resolve(const SceneView<T>& sc, const RenderArgs& a, cudaStream_t st, LaunchInfo* info) {
   PixelMap pm = make_pixel_map(a);
   if (pm.n_pixels == 0) return cudaSuccess;
+  constexpr bool F32 = sizeof(T) == 4;
   // everything in one chunk while it fits 96 KB of shared memory, else 48 KB chunks
-  cudaError_t e = cudaFuncSetAttribute(k_resolve<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RT_SMEM_SHAPE_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(k_resolve<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RT_SMEM_SHAPE_BYTES + 16 * 1024);
   if (e != cudaSuccess) return e;
-  size_t total = (size_t)sc.n_shapes * 12 * sizeof(T);
-  int chunk = total <= 2 * RT_SMEM_SHAPE_BYTES ? (sc.n_shapes > 0 ? sc.n_shapes : 1) : RT_SMEM_SHAPE_BYTES / (12 * (int)sizeof(T));
-  size_t smem = (size_t)chunk * 12 * sizeof(T);
+  const int n_planes = sc.n_shapes - sc.n_spheres;
+  const size_t unit = F32 ? 96 : 12 * sizeof(T);
+  const int n_units = F32 ? sc.n_pairs : sc.n_shapes;
+  const size_t planes_bytes = (F32 && n_planes <= RT_PLANES_SMEM_MAX) ? (size_t)n_planes * 48 : 0;
+  int chunk = (size_t)n_units * unit <= 2 * RT_SMEM_SHAPE_BYTES ? (n_units > 0 ? n_units : 1) : (int)(RT_SMEM_SHAPE_BYTES / unit);
+  size_t smem = planes_bytes + (size_t)chunk * unit;
   long long blocks = (pm.n_pixels + RT_RESOLVE_THREADS - 1) / RT_RESOLVE_THREADS;
   k_resolve<T><<<(unsigned)blocks, RT_RESOLVE_THREADS, smem, st>>>(sc, a, chunk);
   if (info) { info->n_launches += 1; info->variant = 0; }
@@ -235,17 +301,17 @@ template <typename T> struct Level {
 
 template <typename T> struct PtCtx {
   const SceneView<T>* sc;
-  const T* xf;  // inverse transforms of all shapes (shared or global memory)
+  ScanSrc<T> src;  // scan data of all shapes (shared or global memory)
   V3<T> background;
   int N, max_depth, rr_limit;
   unsigned int n_rays;
 };
 
 template <typename T>
-RT_DEV bool trace_closest(const SceneView<T>& sc, const T* xf, const Ray<T>& r, Hit<T>& h) {
+RT_DEV bool trace_closest(const SceneView<T>& sc, const ScanSrc<T>& src, const Ray<T>& r, Hit<T>& h) {
   T best_t = Num<T>::inf();
   int best = -1;
-  scan_closest<T>(xf, 0, sc.n_shapes, sc.n_spheres, sc.orig, r, best_t, best);
+  closest_all<T>(sc, src, r, best_t, best);
   h.idx = -1;
   if (best < 0) return false;
   finish_hit<T>(sc, r, best_t, best, h);
@@ -269,7 +335,7 @@ RT_DEV V3<T> pt_radiance(PtCtx<T>& cx, Ray<T> ray, int depth, Pcg& rng, int* pri
   if (depth > cx.max_depth) return acc;  // render.py:100-101
   while (true) {
     Hit<T> h;
-    bool found = trace_closest<T>(sc, cx.xf, ray, h);
+    bool found = trace_closest<T>(sc, cx.src, ray, h);
     ++cx.n_rays;
     if (first) { if (primary_hit) *primary_hit = found ? sc.orig[h.idx] : -1; first = false; }
     if (!found) {
@@ -325,18 +391,25 @@ template <typename T, int MAXL>
 __global__ void __launch_bounds__(RT_MEGA_THREADS)
 k_pt_mega(const __grid_constant__ SceneView<T> sc, const __grid_constant__ RenderArgs a, const int in_smem) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const T* xf = sc.invm;
+  ScanSrc<T> src = global_src<T>(sc);
   if (in_smem) {
-    T* sh = reinterpret_cast<T*>(smem_raw);
-    stage_shapes(sh, sc.invm, 0, sc.n_shapes);
+    if constexpr (sizeof(T) == 4) {
+      const size_t bytes = (size_t)sc.n_pairs * 96 + (size_t)(sc.n_shapes - sc.n_spheres) * 48;
+      stage_bytes(smem_raw, sc.packed, bytes);
+      src.pairs = reinterpret_cast<const float4*>(smem_raw);
+      src.planes = reinterpret_cast<const float*>(smem_raw) + 24 * (size_t)sc.n_pairs;
+    } else {
+      T* sh = reinterpret_cast<T*>(smem_raw);
+      stage_shapes(sh, sc.invm, 0, sc.n_shapes);
+      src.xf = sh;
+    }
     __syncthreads();
-    xf = sh;
   }
   const PixelMap pm = make_pixel_map(a);
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned int n_samples = 0;
   PtCtx<T> cx;
-  cx.sc = &sc; cx.xf = xf; cx.background = load3<T>(a.background);
+  cx.sc = &sc; cx.src = src; cx.background = load3<T>(a.background);
   cx.N = a.num_of_rays; cx.max_depth = a.max_depth; cx.rr_limit = a.rr_limit; cx.n_rays = 0;
   if (p < pm.n_pixels) {
     int col, row;
@@ -371,7 +444,8 @@ template <typename T>
 cudaError_t launch_pt_mega(const SceneView<T>& sc, const RenderArgs& a, cudaStream_t st, LaunchInfo* info) {
   PixelMap pm = make_pixel_map(a);
   if (pm.n_pixels == 0) return cudaSuccess;
-  size_t bytes = (size_t)sc.n_shapes * 12 * sizeof(T);
+  size_t bytes = sizeof(T) == 4 ? (size_t)sc.n_pairs * 96 + (size_t)(sc.n_shapes - sc.n_spheres) * 48
+                                : (size_t)sc.n_shapes * 12 * sizeof(T);
   int in_smem = bytes <= RT_SMEM_SHAPE_BYTES;
   size_t smem = in_smem ? (bytes ? bytes : 16) : 16;
   long long blocks = (pm.n_pixels + RT_MEGA_THREADS - 1) / RT_MEGA_THREADS;
@@ -404,7 +478,7 @@ RT_DEV V3<T> renderer_call(const SceneView<T>& sc, const RenderArgs& a, const Ra
                            unsigned long long* n_closest, unsigned long long* n_shadow) {
   if (a.algorithm == RT_ALGO_PATHTRACING) {
     PtCtx<T> cx;
-    cx.sc = &sc; cx.xf = sc.invm; cx.background = load3<T>(a.background);
+    cx.sc = &sc; cx.src = global_src<T>(sc); cx.background = load3<T>(a.background);
     cx.N = a.num_of_rays; cx.max_depth = a.max_depth; cx.rr_limit = a.rr_limit; cx.n_rays = 0;
     V3<T> c = (a.num_of_rays == 1) ? pt_radiance<T, 1>(cx, ray, depth, rng, nullptr)
                                    : pt_radiance<T, 64>(cx, ray, depth, rng, nullptr);
@@ -413,7 +487,8 @@ RT_DEV V3<T> renderer_call(const SceneView<T>& sc, const RenderArgs& a, const Ra
   }
   Hit<T> h;
   *n_closest += 1;
-  if (!trace_closest<T>(sc, sc.invm, ray, h)) return load3<T>(a.background);
+  const ScanSrc<T> src = global_src<T>(sc);
+  if (!trace_closest<T>(sc, src, ray, h)) return load3<T>(a.background);
   if (a.algorithm == RT_ALGO_ONOFF) return load3<T>(a.onoff);
   if (a.algorithm == RT_ALGO_FLAT) return flat_color<T>(sc, h);
   const DevMaterial& mat = sc.materials[sc.material[h.idx]];
@@ -421,7 +496,7 @@ RT_DEV V3<T> renderer_call(const SceneView<T>& sc, const RenderArgs& a, const Ra
   for (int l = 0; l < sc.n_lights; ++l) {
     Ray<T> sr = shadow_ray<T>(load3<T>(sc.lights[l].pos), h.point);
     *n_shadow += 1;
-    if (!scan_any<T>(sc.invm, 0, sc.n_shapes, sc.n_spheres, sr)) color = color + light_term<T>(sc, h, ray.d, l);
+    if (!any_all<T>(sc, src, sr)) color = color + light_term<T>(sc, h, ray.d, l);
   }
   return color;
 }
@@ -454,7 +529,7 @@ __global__ void k_probe(const __grid_constant__ SceneView<T> sc, const __grid_co
       memset(&out, 0, sizeof(out));
       T best_t = Num<T>::inf();
       int best = -1;
-      scan_closest<T>(sc.invm, 0, sc.n_shapes, sc.n_spheres, sc.orig, r, best_t, best);
+      closest_all<T>(sc, global_src<T>(sc), r, best_t, best);
       if (best < 0) { out.shape = -1; out.material = -1; }
       else {
         finish_hit<T>(sc, r, best_t, best, h, p.aux != 0, true);
@@ -470,7 +545,7 @@ __global__ void k_probe(const __grid_constant__ SceneView<T> sc, const __grid_co
       if (i >= p.n) return;
       const double* q = p.in + 6 * (size_t)i;
       Ray<T> sr = shadow_ray<T>(mk3<T>((T)q[0], (T)q[1], (T)q[2]), mk3<T>((T)q[3], (T)q[4], (T)q[5]));
-      p.flags[i] = scan_any<T>(sc.invm, 0, sc.n_shapes, sc.n_spheres, sr) ? 0 : 1;
+      p.flags[i] = any_all<T>(sc, global_src<T>(sc), sr) ? 0 : 1;
       return;
     }
     case PROBE_PIGMENT: {

@@ -47,12 +47,12 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* xf = sc.invm;
+  ScanSrc<float> src = global_src<float>(sc);
   if (SHAPES_SMEM) {
-    float* sh = reinterpret_cast<float*>(smem_raw);
-    stage_shapes(sh, sc.invm, 0, sc.n_shapes);
+    stage_bytes(smem_raw, sc.packed, (size_t)sc.n_pairs * 96 + (size_t)(sc.n_shapes - sc.n_spheres) * 48);
     __syncthreads();
-    xf = sh;
+    src.pairs = reinterpret_cast<const float4*>(smem_raw);
+    src.planes = reinterpret_cast<const float*>(smem_raw) + 24 * (size_t)sc.n_pairs;
   }
   unsigned char* wbase = smem_raw + cfg.shape_bytes + (size_t)warp * cfg.per_warp_bytes;
   ScatterRec* stack = reinterpret_cast<ScatterRec*>(wbase);
@@ -184,7 +184,7 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
         ScatterRec out;
         if (active) {
           Hit<float> h;
-          const bool found = trace_closest<float>(sc, xf, ray, h);
+          const bool found = trace_closest<float>(sc, src, ray, h);
           ++n_rays;
           if (count_rays) {
             if (MULTI_SLOT) atomicAdd(&slot_rays[slot], 1);
@@ -305,7 +305,7 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   long long cap = a.num_of_rays == 1 ? 64 : 32ll * ((long long)a.max_depth + 1);
   if (cap < 64) cap = 64;
   const bool multi = cfg.group > 1;
-  size_t shape_bytes = (size_t)sc.n_shapes * 48;
+  size_t shape_bytes = (size_t)sc.n_pairs * 96 + (size_t)(sc.n_shapes - sc.n_spheres) * 48;
   const bool shapes_smem = shape_bytes > 0 && shape_bytes <= 64 * 1024;
   cfg.shape_bytes = shapes_smem ? (int)((shape_bytes + 15) / 16 * 16) : 0;
   const size_t limit = 200 * 1024;
