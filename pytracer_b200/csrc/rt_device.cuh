@@ -169,7 +169,7 @@ RT_DEV float sphere_qdelta(const float* __restrict__ im, const Ray<float>& r, fl
   a = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
   hb = fmaf(px, dx, fmaf(py, dy, pz * dz));
   const float c = fmaf(px, px, fmaf(py, py, fmaf(pz, pz, -1.0f)));
-  return __fsub_rn(__fmul_rn(hb, hb), __fmul_rn(a, c));  // unfused: bit-identical to the packed sweep
+  return fmaf(hb, hb, -(a * c));  // same rounding as the packed sweep (ptxas fuses its sub into FFMA2 with -ac)
 }
 
 // roots of the crossed sphere: t = (-b/2 -+ sqrt(delta/4)) / a, first one inside (tmin, tmax)
@@ -228,9 +228,22 @@ RT_DEV f32x2 pair_qdelta(const float4* __restrict__ q, const PackedRay& r) {
 
 // Sweeps sphere pairs [p0, p1) whose data starts at `pairs` (pairs[0] = pair `base`); crossed spheres
 // are appended to cand[] (ring of RT_CAND_CAP; nc counts all of them) as sorted sphere indices.
+template <bool UNROLL2 = true>
 RT_DEV void sweep_pairs(const float4* __restrict__ pairs, int base, int p0, int p1, const PackedRay& r,
                         int* cand, int& nc) {
   int p = p0;
+  if (!UNROLL2) {  // few spheres (e.g. demo.txt): one pair at a time keeps the register count low
+#pragma unroll 1
+    for (; p < p1; ++p) {
+      float a0, a1;
+      upk2(pair_qdelta(pairs + 6 * (p - base), r), a0, a1);
+      if (fmaxf(a0, a1) > 0.0f) {
+        if (a0 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = 2 * p; ++nc; }
+        if (a1 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = 2 * p + 1; ++nc; }
+      }
+    }
+    return;
+  }
   for (; p + 2 <= p1; p += 2) {
     const float4* q = pairs + 6 * (p - base);
     float a0, a1, b0, b1;
@@ -342,17 +355,22 @@ template <typename T>
 RT_DEV void closest_all(const SceneView<T>& sc, const ScanSrc<T>& src, const Ray<T>& r, T& best_t, int& best) {
   scan_closest<T>(src.xf, 0, sc.n_shapes, sc.n_spheres, sc.orig, r, best_t, best);
 }
-template <>
-RT_DEV void closest_all<float>(const SceneView<float>& sc, const ScanSrc<float>& src, const Ray<float>& r,
-                               float& best_t, int& best) {
+template <bool UNROLL2>
+RT_DEV void closest_all_f32(const SceneView<float>& sc, const ScanSrc<float>& src, const Ray<float>& r,
+                            float& best_t, int& best) {
   if (sc.n_pairs > 0) {
     int cand[RT_CAND_CAP];
     int nc = 0;
     const PackedRay pr = pack_ray(r);
-    sweep_pairs(src.pairs, 0, 0, sc.n_pairs, pr, cand, nc);
+    sweep_pairs<UNROLL2>(src.pairs, 0, 0, sc.n_pairs, pr, cand, nc);
     resolve_candidates(sc.invm, sc.n_spheres, cand, nc, r, best_t, best);
   }
   scan_plane_block(src.planes, sc.n_spheres, sc.n_shapes - sc.n_spheres, sc.orig, r, best_t, best);
+}
+template <>
+RT_DEV void closest_all<float>(const SceneView<float>& sc, const ScanSrc<float>& src, const Ray<float>& r,
+                               float& best_t, int& best) {
+  closest_all_f32<true>(sc, src, r, best_t, best);
 }
 
 // World.is_point_visible's loop (world.py:76-78): does any shape block the segment?

@@ -40,8 +40,11 @@ RT_DEV int own_stratum(const RenderArgs& a, int ls) {
   return (a.part_mode == RT_PART_SPP && a.part_count > 1) ? a.part_rank + ls * a.part_count : ls;
 }
 
-template <bool SHAPES_SMEM, bool MULTI_SLOT>
-__global__ void __launch_bounds__(RT_WARP_MAX_THREADS, 2)
+// SMALL: scenes of at most 8 spheres (demo.txt): the sweep is not unrolled and the kernel is held to
+// 80 registers so that three CTAs (24 warps) fit an SM; large scenes are FMA-bound in the unrolled
+// sweep and keep the 128-register budget.
+template <bool SHAPES_SMEM, bool MULTI_SLOT, bool SMALL>
+__global__ void __launch_bounds__(RT_WARP_MAX_THREADS, SMALL ? 3 : 2)
 k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ RenderArgs a,
           const __grid_constant__ WarpCfg cfg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -184,7 +187,11 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
         ScatterRec out;
         if (active) {
           Hit<float> h;
-          const bool found = trace_closest<float>(sc, src, ray, h);
+          float best_t = Num<float>::inf();
+          int best = -1;
+          closest_all_f32<!SMALL>(sc, src, ray, best_t, best);
+          const bool found = best >= 0;
+          if (found) finish_hit<float>(sc, ray, best_t, best, h);
           ++n_rays;
           if (count_rays) {
             if (MULTI_SLOT) atomicAdd(&slot_rays[slot], 1);
@@ -321,8 +328,10 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   cfg.per_warp_bytes = (int)per_warp;
 
   void (*kern)(const SceneView<float>, const RenderArgs, const WarpCfg);
-  if (shapes_smem) kern = multi ? k_pt_warp<true, true> : k_pt_warp<true, false>;
-  else kern = multi ? k_pt_warp<false, true> : k_pt_warp<false, false>;
+  const bool small = sc.n_spheres <= 8 && shapes_smem;
+  if (small) kern = multi ? k_pt_warp<true, true, true> : k_pt_warp<true, false, true>;
+  else if (shapes_smem) kern = multi ? k_pt_warp<true, true, false> : k_pt_warp<true, false, false>;
+  else kern = multi ? k_pt_warp<false, true, false> : k_pt_warp<false, false, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
