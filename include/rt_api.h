@@ -244,6 +244,12 @@ int rt_scatter(rt_scene* scene, int32_t material, int32_t precision, const doubl
 /* create_onb_from_z, geometry.py:247-262: normals double[n][3] -> double[n][9] = e1,e2,e3 */
 int rt_onb(int32_t precision, const double* normals, int32_t n, double* out);
 
+/* ---- host buffers ----
+ * Page-locks / unlocks a caller-owned host buffer (cudaHostRegister) so that rt_render's final
+ * device->host copy of the image runs at full PCIe speed.  Optional: pageable buffers work too. */
+int rt_host_register(void* ptr, uint64_t bytes);
+int rt_host_unregister(void* ptr);
+
 /* ---- measurement aid: FP32 FMA roofline denominator measured on this device ----
  * Runs a register-resident FFMA chain kernel (8 independent accumulators per thread, grid sized to
  * fill every SM) and reports achieved TFLOP/s (2 flops per FMA) and the kernel time. */

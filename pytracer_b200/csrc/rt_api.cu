@@ -610,3 +610,19 @@ extern "C" int rt_bench_ffma(int32_t iterations, double* tflops, float* ms_out) 
   if (ms_out) *ms_out = ms;
   return RT_OK;
 }
+
+extern "C" int rt_host_register(void* ptr, uint64_t bytes) {
+  if (!ptr || bytes == 0) return fail(RT_ERR_INVALID, "rt_host_register: bad argument");
+  if (rt_device_count() <= 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
+  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return RT_OK; }
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
+  return RT_OK;
+}
+
+extern "C" int rt_host_unregister(void* ptr) {
+  if (!ptr) return fail(RT_ERR_INVALID, "rt_host_unregister: bad argument");
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(RT_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
+  return RT_OK;
+}

@@ -64,6 +64,34 @@ class HdrImage:
     def rgb_array(self) -> np.ndarray:
         return self._rgb
 
+    def pin(self) -> bool:
+        """Page-lock the pixel buffer (once) so the device->host copy of a render runs at PCIe speed.
+        Returns False when the buffer cannot be pinned (no device, tiny image): copies still work."""
+        if getattr(self, "_pinned_ptr", None) == self._rgb.ctypes.data:
+            return True
+        if self._rgb.nbytes < (1 << 16):
+            return False
+        try:
+            from . import _native
+
+            lib = _native.load()
+            if lib.rt_host_register(self._rgb.ctypes.data, self._rgb.nbytes) != 0:
+                return False
+        except Exception:
+            return False
+        self._pinned_ptr = self._rgb.ctypes.data
+        return True
+
+    def __del__(self):
+        ptr = getattr(self, "_pinned_ptr", None)
+        if ptr:
+            try:
+                from . import _native
+
+                _native.load().rt_host_unregister(ptr)
+            except Exception:
+                pass
+
     @property
     def pixels(self) -> PixelView:
         return PixelView(self._rgb)

@@ -80,6 +80,8 @@ class ImageTracer:
     def _adoptable_buffer(self) -> Optional[np.ndarray]:
         arr = getattr(self.image, "_rgb", None)
         if isinstance(arr, np.ndarray) and arr.dtype == np.float32 and arr.flags.c_contiguous:
+            if hasattr(self.image, "pin"):
+                self.image.pin()
             return arr
         return None
 
