@@ -5,7 +5,7 @@ set -euo pipefail
 cd "$(dirname "$0")"
 OUT=../libpytracer_b200.so
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC"
+COMMON="${RT_EXTRA_FLAGS:-} -O3 -std=c++17 -lineinfo -Xcompiler -fPIC"
 mkdir -p build
 nvcc $ARCH $COMMON -c rt_kernels_f32.cu -o build/rt_kernels_f32.o &
 nvcc $ARCH $COMMON --fmad=false -c rt_kernels_f64.cu -o build/rt_kernels_f64.o &

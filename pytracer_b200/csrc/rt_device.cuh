@@ -266,26 +266,35 @@ RT_DEV void sweep_pairs(const float4* __restrict__ pairs, int base, int p0, int 
 
 // Exact roots for the crossed spheres only, from the plain [n][12] array in global memory (a few per
 // ray: L1/L2 hits).  Ascending index + strict '<' keeps the first shape on ties (world.py:62).
+//
+// `origin` = sorted index of the shape the ray starts on (-1: none).  A ray that starts ON a sphere
+// has c = |o|^2 - 1 = 0: its roots are t = 0 (never inside (tmin, tmax): the fp64 reference gets
+// ~1e-16 there) and t = -b/a.  In fp32 c is ~1e-7 instead of 0 and, for grazing rays, the first root
+// lands at t ~ 1e-4 > tmin — a phantom re-hit that makes a mirror sphere reflect into itself.  For the
+// origin sphere the exact second root -2(b/2)/a is used instead: what the reference computes, without
+// the cancellation.
+RT_DEV float sphere_t_at(const float* __restrict__ im, const Ray<float>& r, bool is_origin) {
+  float a, hb;
+  const float qd = sphere_qdelta(im, r, a, hb);
+  if (is_origin) {
+    const float t = -2.0f * hb * fast_rcp(a);
+    return (t > r.tmin && t < r.tmax) ? t : Num<float>::inf();
+  }
+  return qd > 0.0f ? sphere_root(a, hb, qd, r.tmin, r.tmax) : Num<float>::inf();
+}
+
 RT_DEV void resolve_candidates(const float* __restrict__ invm, int n_spheres, const int* cand, int nc,
-                               const Ray<float>& r, float& best_t, int& best) {
+                               const Ray<float>& r, float& best_t, int& best, int origin = -1) {
   if (nc <= RT_CAND_CAP) {
     for (int j = 0; j < nc; ++j) {
       const int i = cand[j];
-      float a, hb;
-      const float qd = sphere_qdelta(invm + 12 * (size_t)i, r, a, hb);
-      if (qd > 0.0f) {
-        const float t = sphere_root(a, hb, qd, r.tmin, r.tmax);
-        if (t < best_t) { best_t = t; best = i; }
-      }
+      const float t = sphere_t_at(invm + 12 * (size_t)i, r, i == origin);
+      if (t < best_t) { best_t = t; best = i; }
     }
   } else {  // a line through more than RT_CAND_CAP spheres: plain pass
     for (int i = 0; i < n_spheres; ++i) {
-      float a, hb;
-      const float qd = sphere_qdelta(invm + 12 * (size_t)i, r, a, hb);
-      if (qd > 0.0f) {
-        const float t = sphere_root(a, hb, qd, r.tmin, r.tmax);
-        if (t < best_t) { best_t = t; best = i; }
-      }
+      const float t = sphere_t_at(invm + 12 * (size_t)i, r, i == origin);
+      if (t < best_t) { best_t = t; best = i; }
     }
   }
 }
@@ -312,11 +321,14 @@ RT_DEV bool any_candidate_blocks(const float* __restrict__ invm, int n_spheres, 
 }
 
 // planes [0, n_planes) at `planes` (12 floats each; sorted index = n_spheres + k)
+// (a ray that starts on a plane cannot meet it again: exact t = 0; the origin plane is skipped)
 RT_DEV void scan_plane_block(const float* __restrict__ planes, int n_spheres, int n_planes,
-                             const int32_t* __restrict__ orig, const Ray<float>& r, float& best_t, int& best) {
+                             const int32_t* __restrict__ orig, const Ray<float>& r, float& best_t, int& best,
+                             int origin = -1) {
   for (int k = 0; k < n_planes; ++k) {
-    const float t = plane_t<float>(planes + 12 * k, r);
     const int i = n_spheres + k;
+    if (i == origin) continue;
+    const float t = plane_t<float>(planes + 12 * k, r);
     if (t < best_t) { best_t = t; best = i; }
     else if (t == best_t && best >= 0 && best < n_spheres) {
       if (plane_wins_tie(orig, i, best)) { best_t = t; best = i; }
@@ -351,26 +363,28 @@ template <> RT_DEV ScanSrc<float> global_src<float>(const SceneView<float>& sc) 
 }
 
 // World.ray_intersection's loop over ALL shapes (world.py:55-64): index of the winner, -1 = miss
+// (`origin`, the shape a scattered ray starts on, is used by the fp32 path only — see resolve_candidates;
+// the fp64 path evaluates every shape exactly like the reference does)
 template <typename T>
-RT_DEV void closest_all(const SceneView<T>& sc, const ScanSrc<T>& src, const Ray<T>& r, T& best_t, int& best) {
+RT_DEV void closest_all(const SceneView<T>& sc, const ScanSrc<T>& src, const Ray<T>& r, T& best_t, int& best, int origin = -1) {
   scan_closest<T>(src.xf, 0, sc.n_shapes, sc.n_spheres, sc.orig, r, best_t, best);
 }
 template <bool UNROLL2>
 RT_DEV void closest_all_f32(const SceneView<float>& sc, const ScanSrc<float>& src, const Ray<float>& r,
-                            float& best_t, int& best) {
+                            float& best_t, int& best, int origin = -1) {
   if (sc.n_pairs > 0) {
     int cand[RT_CAND_CAP];
     int nc = 0;
     const PackedRay pr = pack_ray(r);
     sweep_pairs<UNROLL2>(src.pairs, 0, 0, sc.n_pairs, pr, cand, nc);
-    resolve_candidates(sc.invm, sc.n_spheres, cand, nc, r, best_t, best);
+    resolve_candidates(sc.invm, sc.n_spheres, cand, nc, r, best_t, best, origin);
   }
-  scan_plane_block(src.planes, sc.n_spheres, sc.n_shapes - sc.n_spheres, sc.orig, r, best_t, best);
+  scan_plane_block(src.planes, sc.n_spheres, sc.n_shapes - sc.n_spheres, sc.orig, r, best_t, best, origin);
 }
 template <>
 RT_DEV void closest_all<float>(const SceneView<float>& sc, const ScanSrc<float>& src, const Ray<float>& r,
-                               float& best_t, int& best) {
-  closest_all_f32<true>(sc, src, r, best_t, best);
+                               float& best_t, int& best, int origin) {
+  closest_all_f32<true>(sc, src, r, best_t, best, origin);
 }
 
 // World.is_point_visible's loop (world.py:76-78): does any shape block the segment?

@@ -296,7 +296,7 @@ cudaError_t launch_resolve(const SceneView<T>& sc, const RenderArgs& a, cudaStre
 // ---------------------------------------------------------------- PathTracer, depth-first
 template <typename T> struct Level {
   V3<T> P, nd, w;  // hit point; normal (diffuse) or mirror direction (specular); throughput of a child
-  int remaining, depth, kind;
+  int remaining, depth, kind, origin;  // origin: sorted index of the shape the children start on
 };
 
 template <typename T> struct PtCtx {
@@ -308,10 +308,10 @@ template <typename T> struct PtCtx {
 };
 
 template <typename T>
-RT_DEV bool trace_closest(const SceneView<T>& sc, const ScanSrc<T>& src, const Ray<T>& r, Hit<T>& h) {
+RT_DEV bool trace_closest(const SceneView<T>& sc, const ScanSrc<T>& src, const Ray<T>& r, Hit<T>& h, int origin = -1) {
   T best_t = Num<T>::inf();
   int best = -1;
-  closest_all<T>(sc, src, r, best_t, best);
+  closest_all<T>(sc, src, r, best_t, best, origin);
   h.idx = -1;
   if (best < 0) return false;
   finish_hit<T>(sc, r, best_t, best, h);
@@ -332,10 +332,11 @@ RT_DEV V3<T> pt_radiance(PtCtx<T>& cx, Ray<T> ray, int depth, Pcg& rng, int* pri
   V3<T> thr = mk3<T>((T)1, (T)1, (T)1);
   const T inv_n = (T)1 / (T)cx.N;
   bool first = true;
+  int origin = -1;
   if (depth > cx.max_depth) return acc;  // render.py:100-101
   while (true) {
     Hit<T> h;
-    bool found = trace_closest<T>(sc, cx.src, ray, h);
+    bool found = trace_closest<T>(sc, cx.src, ray, h, origin);
     ++cx.n_rays;
     if (first) { if (primary_hit) *primary_hit = found ? sc.orig[h.idx] : -1; first = false; }
     if (!found) {
@@ -361,6 +362,7 @@ RT_DEV V3<T> pt_radiance(PtCtx<T>& cx, Ray<T> ray, int depth, Pcg& rng, int* pri
           L.w = inv_n * mul3(thr, hit_color);
           L.remaining = cx.N;
           L.depth = depth + 1;
+          L.origin = h.idx;
         } else if (mat.brdf_kind == RT_BRDF_DIFFUSE) {
           // the reference still scatters N rays here and cuts them at depth > max_depth
           pcg_skip(rng, 2u * (unsigned)cx.N);
@@ -382,6 +384,7 @@ RT_DEV V3<T> pt_radiance(PtCtx<T>& cx, Ray<T> ray, int depth, Pcg& rng, int* pri
     }
     thr = L.w;
     depth = L.depth;
+    origin = L.origin;
     if (--L.remaining == 0) --top;  // the slot is free for the child's own level
   }
   return acc;

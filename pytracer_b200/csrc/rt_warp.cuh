@@ -20,8 +20,9 @@
 
 #define RT_WARP_MAX_THREADS 256
 
+
 struct __align__(16) ScatterRec {
-  float4 a;  // P.xyz, meta (slot | kind << 5 | child depth << 8)
+  float4 a;  // P.xyz, meta (slot | kind << 5 | child depth << 6 (10 bits) | origin shape << 16 (0xFFFF: none))
   float4 b;  // nd.xyz (normal, or mirror direction for a specular surface), w.r
   float4 c;  // w.g, w.b, rng state lo, hi
 };
@@ -43,7 +44,16 @@ RT_DEV int own_stratum(const RenderArgs& a, int ls) {
 // SMALL: scenes of at most 8 spheres (demo.txt): the sweep is not unrolled and the kernel is held to
 // 80 registers so that three CTAs (24 warps) fit an SM; large scenes are FMA-bound in the unrolled
 // sweep and keep the 128-register budget.
-template <bool SHAPES_SMEM, bool MULTI_SLOT, bool SMALL>
+// ACC: how per-pixel sums are kept while a task is in flight.
+//   ACC_REG   one pixel per task: lane-private registers, one warp reduction at the end
+//   ACC_LANES 2..8 pixels per task: acc[slot][channel][lane] in shared memory — every lane adds into
+//             its own column (no conflicts, no atomics), reduced over lanes at the end
+//   ACC_SEG   more pixels per task: segmented warp scan over the lanes of a record, then one
+//             shared-memory atomic per record
+enum { ACC_REG = 0, ACC_LANES = 1, ACC_SEG = 2 };
+#define RT_ACC_LANES_MAX_GROUP 8
+
+template <bool SHAPES_SMEM, int ACC, bool SMALL>
 __global__ void __launch_bounds__(RT_WARP_MAX_THREADS, SMALL ? 3 : 2)
 k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ RenderArgs a,
           const __grid_constant__ WarpCfg cfg) {
@@ -60,8 +70,9 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
   unsigned char* wbase = smem_raw + cfg.shape_bytes + (size_t)warp * cfg.per_warp_bytes;
   ScatterRec* stack = reinterpret_cast<ScatterRec*>(wbase);
   ScatterRec* cur = stack + cfg.cap;
-  float* acc = reinterpret_cast<float*>(cur + 1);  // [32][3], MULTI_SLOT only
-  int* slot_rays = reinterpret_cast<int*>(acc + 96);  // [32], MULTI_SLOT + RT_HIT_RAY_COUNT only
+  constexpr bool MULTI_SLOT = ACC != ACC_REG;
+  int* slot_rays = reinterpret_cast<int*>(cur + 1);        // [32], multi-pixel tasks + RT_HIT_RAY_COUNT
+  float* acc = reinterpret_cast<float*>(slot_rays + 32);   // ACC_SEG: [32][3]; ACC_LANES: [G][3][32]
   const bool count_rays = a.out_hit != nullptr && a.hit_mode == RT_HIT_RAY_COUNT;
 
   const PixelMap pm = make_pixel_map(a);
@@ -86,7 +97,8 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
     float sr = 0.f, sg = 0.f, sb = 0.f;  // lane-private sums (single-slot tasks)
     unsigned int task_rays = 0;
     if (MULTI_SLOT) {
-      for (int i = lane; i < 96; i += 32) acc[i] = 0.f;
+      if (ACC == ACC_SEG) { for (int i = lane; i < 96; i += 32) acc[i] = 0.f; }
+      else { for (int i = 0; i < 3 * cfg.group; ++i) acc[i * 32 + lane] = 0.f; }
       slot_rays[lane] = 0;
       __syncwarp();
     }
@@ -97,7 +109,7 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
       while (true) {
         // ---------------- pick this lane's ray
         bool active;
-        int slot = 0, depth = 0, seg_start = lane;
+        int slot = 0, depth = 0, seg_start = lane, origin = -1;
         V3<float> thr = mk3<float>(1.f, 1.f, 1.f);
         Ray<float> ray;
         Pcg rng;
@@ -123,7 +135,7 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
             last_of_pixel = (ls == L - 1);
             ++n_samples;
           }
-          if (MULTI_SLOT) seg_start = max(0, slot * L - round * 32);
+          if (ACC == ACC_SEG) seg_start = max(0, slot * L - round * 32);
         } else {
           const long long avail = (long long)cur_rem + (long long)top * N;
           if (avail == 0) break;
@@ -161,7 +173,9 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
           if (active) {
             const int meta = __float_as_int(rec.a.w);
             slot = meta & 31;
-            depth = meta >> 8;
+            depth = (meta >> 6) & 1023;
+            origin = (int)((unsigned)meta >> 16);
+            if (origin == 0xFFFF) origin = -1;
             thr = mk3<float>(rec.b.w, rec.c.x, rec.c.y);
             const uint64_t base = ((uint64_t)__float_as_uint(rec.c.w) << 32) | (uint64_t)__float_as_uint(rec.c.z);
             rng.state = mix64(base + (uint64_t)(child + 1) * 0x9E3779B97F4A7C15ULL);
@@ -189,7 +203,7 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
           Hit<float> h;
           float best_t = Num<float>::inf();
           int best = -1;
-          closest_all_f32<!SMALL>(sc, src, ray, best_t, best);
+          closest_all_f32<!SMALL>(sc, src, ray, best_t, best, origin);
           const bool found = best >= 0;
           if (found) finish_hit<float>(sc, ray, best_t, best, h);
           ++n_rays;
@@ -218,7 +232,8 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
               const V3<float> nd = (mat.brdf_kind == RT_BRDF_DIFFUSE) ? h.normal : specular_dir<float>(ray.d, h.normal);
               const V3<float> w = inv_n * mul3(thr, hit_color);
               out.a = make_float4(h.point.x, h.point.y, h.point.z,
-                                  __int_as_float(slot | (mat.brdf_kind << 5) | ((depth + 1) << 8)));
+                                  __int_as_float(slot | (mat.brdf_kind << 5) | ((depth + 1) << 6) |
+                                                 ((h.idx < 0xFFFF ? h.idx : 0xFFFF) << 16)));
               out.b = make_float4(nd.x, nd.y, nd.z, w.x);
               out.c = make_float4(w.y, w.z, __uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)));
             }
@@ -226,7 +241,7 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
         }
 
         // ---------------- accumulate
-        if (MULTI_SLOT) {
+        if (ACC == ACC_SEG) {
           // lanes of one record (or one pixel, for primaries) are contiguous: segmented scan
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
@@ -241,6 +256,11 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
             atomicAdd(&acc[3 * slot + 0], contrib.x);
             atomicAdd(&acc[3 * slot + 1], contrib.y);
             atomicAdd(&acc[3 * slot + 2], contrib.z);
+          }
+        } else if (ACC == ACC_LANES) {
+          if (active) {  // this lane's own column of the pixel's accumulator: no other lane touches it
+            float* col = acc + (3 * slot) * 32 + lane;
+            col[0] += contrib.x; col[32] += contrib.y; col[64] += contrib.z;
           }
         } else {
           sr += contrib.x; sg += contrib.y; sb += contrib.z;
@@ -261,7 +281,7 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
     }
 
     // ---------------- write the pixels of this task
-    if (MULTI_SLOT) {
+    if (ACC == ACC_SEG) {
       __syncwarp();
       const long long p = p0 + lane;
       if (lane < G && p < pm.n_pixels) {
@@ -270,6 +290,25 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
         store_pixel<float>(a, (long long)row * a.width + col,
                            mk3<float>(acc[3 * lane] * inv_spp, acc[3 * lane + 1] * inv_spp, acc[3 * lane + 2] * inv_spp));
         if (count_rays) a.out_hit[(long long)row * a.width + col] = slot_rays[lane];
+      }
+      __syncwarp();
+    } else if (ACC == ACC_LANES) {
+      __syncwarp();
+      for (int g = 0; g < G; ++g) {
+        float r = acc[(3 * g) * 32 + lane], gr = acc[(3 * g + 1) * 32 + lane], b = acc[(3 * g + 2) * 32 + lane];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          r += __shfl_xor_sync(FULL, r, d);
+          gr += __shfl_xor_sync(FULL, gr, d);
+          b += __shfl_xor_sync(FULL, b, d);
+        }
+        const long long p = p0 + g;
+        if (lane == 0 && p < pm.n_pixels) {
+          int col, row;
+          pm.locate(p, col, row);
+          store_pixel<float>(a, (long long)row * a.width + col, mk3<float>(r * inv_spp, gr * inv_spp, b * inv_spp));
+          if (count_rays) a.out_hit[(long long)row * a.width + col] = slot_rays[g];
+        }
       }
       __syncwarp();
     } else {
@@ -302,7 +341,7 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
     L = a.part_rank < S2 ? (S2 - a.part_rank + a.part_count - 1) / a.part_count : 0;
   if (pm.n_pixels == 0 || L == 0) return cudaSuccess;
   if (a.num_of_rays < 1) { *why_not = "num_of_rays must be >= 1"; return cudaErrorInvalidValue; }
-  if (a.max_depth >= (1 << 22)) { *why_not = "max_depth too large for the warp variant"; return cudaErrorInvalidValue; }
+  if (a.max_depth >= 1023) { *why_not = "max_depth >= 1023 is not supported by the warp variant (use mega)"; return cudaErrorInvalidValue; }
   WarpCfg cfg;
   cfg.per_pixel = L;
   cfg.group = L >= 32 ? 1 : 32 / L;
@@ -311,7 +350,7 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   // at most ~32 records per tree level are alive at any time, one level if N == 1
   long long cap = a.num_of_rays == 1 ? 64 : 32ll * ((long long)a.max_depth + 1);
   if (cap < 64) cap = 64;
-  const bool multi = cfg.group > 1;
+  const int acc_mode = cfg.group == 1 ? ACC_REG : (cfg.group <= RT_ACC_LANES_MAX_GROUP ? ACC_LANES : ACC_SEG);
   size_t shape_bytes = (size_t)sc.n_pairs * 96 + (size_t)(sc.n_shapes - sc.n_spheres) * 48;
   const bool shapes_smem = shape_bytes > 0 && shape_bytes <= 64 * 1024;
   cfg.shape_bytes = shapes_smem ? (int)((shape_bytes + 15) / 16 * 16) : 0;
@@ -319,7 +358,9 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   int warps = RT_WARP_MAX_THREADS / 32;
   size_t per_warp = 0, smem = 0;
   for (;; warps >>= 1) {
-    per_warp = (size_t)(cap + 1) * sizeof(ScatterRec) + (multi ? 96 * sizeof(float) + 32 * sizeof(int) : 0);
+    per_warp = (size_t)(cap + 1) * sizeof(ScatterRec);
+    if (acc_mode == ACC_SEG) per_warp += 32 * sizeof(int) + 96 * sizeof(float);
+    if (acc_mode == ACC_LANES) per_warp += 32 * sizeof(int) + (size_t)cfg.group * 96 * sizeof(float);
     smem = cfg.shape_bytes + per_warp * warps;
     if (smem <= limit || warps == 1) break;
   }
@@ -329,9 +370,12 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
 
   void (*kern)(const SceneView<float>, const RenderArgs, const WarpCfg);
   const bool small = sc.n_spheres <= 8 && shapes_smem;
-  if (small) kern = multi ? k_pt_warp<true, true, true> : k_pt_warp<true, false, true>;
-  else if (shapes_smem) kern = multi ? k_pt_warp<true, true, false> : k_pt_warp<true, false, false>;
-  else kern = multi ? k_pt_warp<false, true, false> : k_pt_warp<false, false, false>;
+#define RT_PICK(ACCM)                                                                   \
+  (small ? k_pt_warp<true, ACCM, true> : (shapes_smem ? k_pt_warp<true, ACCM, false> : k_pt_warp<false, ACCM, false>))
+  if (acc_mode == ACC_REG) kern = RT_PICK(ACC_REG);
+  else if (acc_mode == ACC_LANES) kern = RT_PICK(ACC_LANES);
+  else kern = RT_PICK(ACC_SEG);
+#undef RT_PICK
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
   if (e != cudaSuccess) return e;
   int per_sm = 0;

@@ -88,7 +88,8 @@ def _render_share_cuda(scene, p: _abi.rt_render_params):
     return image, scene.finish(stream)
 
 
-def render_partitioned(scene, params: _abi.rt_render_params, comm, render_share=_render_share_cuda) -> Tuple[np.ndarray, dict]:
+def render_partitioned(scene, params: _abi.rt_render_params, comm, render_share=_render_share_cuda,
+                       out: Optional[np.ndarray] = None) -> Tuple[np.ndarray, dict]:
     """This rank's share on its GPU, ONE all-reduce(sum) of the fp32 image, image to the host.
     ``render_share(scene, partitioned_params) -> (tensor, stats)`` is injectable so that the exchange
     logic can be exercised on CPU (gloo) with the oracle standing in for the GPU."""
@@ -101,4 +102,7 @@ def render_partitioned(scene, params: _abi.rt_render_params, comm, render_share=
     comm.all_reduce_sum(counts)
     stats = dict(stats)
     stats["rays_closest"], stats["rays_shadow"], stats["samples"] = (int(v) for v in counts.tolist())
+    if out is not None and out.dtype == np.float32 and out.shape == tuple(image.shape) and out.flags.c_contiguous:
+        torch.from_numpy(out).copy_(image)  # straight into the caller's (page-locked) framebuffer
+        return out, stats
     return image.cpu().numpy(), stats

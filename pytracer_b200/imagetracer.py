@@ -69,7 +69,7 @@ class ImageTracer:
         if comm is not None and comm.world_size > 1:
             from .dist import render_partitioned
 
-            rgb, stats = render_partitioned(scene, self._params(renderer), comm)
+            rgb, stats = render_partitioned(scene, self._params(renderer), comm, out=self._adoptable_buffer())
         else:
             rgb, _, stats = scene.render(self._params(renderer), out=self._adoptable_buffer())
         self.last_stats = renderer.last_stats = stats
