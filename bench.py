@@ -200,6 +200,8 @@ def run_ours(args, rank, local_rank, world_size):
     params = build_params(kw, camera, variant=args.variant, precision=args.precision)
     if world_size > 1:
         params = partition_params(params, rank, world_size)
+        if args.partition != "auto":
+            params.part_mode = _abi.PARTITIONS[args.partition]
     H, W = params.height, params.width
     image = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB of L2
@@ -281,8 +283,13 @@ def run_ours(args, rank, local_rank, world_size):
     achieved_tf = rays_per_launch_rank * flops_per_ray / (k_ms * 1e-3) / 1e12
     prop = torch.cuda.get_device_properties(local_rank)
     nominal_tf = prop.multi_processor_count * 128 * 2 * 1.965e9 / 1e12
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload if SCALE == 1 and world_size == 1 else "")
+    except Exception:
+        pass
     roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "traffic": None, "peak_source": "FFMA micro-benchmark run in this job (rt_bench_ffma); MEASURED_PEAKS.json holds "
+                "traffic": traffic, "peak_source": "FFMA micro-benchmark run in this job (rt_bench_ffma); MEASURED_PEAKS.json holds "
                 "only HBM and bf16-tensor peaks, neither bounds this path", "peak_nominal": nominal_tf,
                 "flops_per_ray": flops_per_ray, "kernel_ms": k_ms, "rays_per_launch": rays_per_launch_rank}
     line = {
@@ -311,6 +318,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"])
     ap.add_argument("--variant", default="auto", choices=["auto", "mega", "warp"])
     ap.add_argument("--precision", default="auto", choices=["auto", "f32", "f64"])
+    ap.add_argument("--partition", default="auto", choices=["auto", "spp", "rows"],
+                    help="multi-GPU split: strata of every pixel (path tracing default) or interleaved rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scale", type=int, default=1, help="divide width and height by this (quick experiments only; "
                     "a scaled run is NOT the benchmark and says so in config)")
