@@ -103,8 +103,12 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
       __syncwarp();
     }
 
-    for (int round = 0; round < cfg.rounds; ++round) {
+    // All samples of the task start first (cfg.rounds warp-wide primary iterations pushing onto one
+    // stack), then the stack drains once: the partially filled iterations at the end of a drain are
+    // paid once per task instead of once per 32 samples.
+    {
       int top = 0, cur_rem = 0, cur_done = 0;
+      int round = 0;
       bool primary_phase = true;
       while (true) {
         // ---------------- pick this lane's ray
@@ -276,7 +280,7 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
         }
         if (top + npush <= cfg.cap) top += npush;
         __syncwarp();
-        primary_phase = false;
+        if (primary_phase && ++round >= cfg.rounds) primary_phase = false;
       }
     }
 
@@ -344,11 +348,19 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   if (a.max_depth >= 1023) { *why_not = "max_depth >= 1023 is not supported by the warp variant (use mega)"; return cudaErrorInvalidValue; }
   WarpCfg cfg;
   cfg.per_pixel = L;
-  cfg.group = L >= 32 ? 1 : 32 / L;
+  // pixels per task: one when a pixel alone fills the warp; up to 8 (>= 64 samples per task) while
+  // lane-private accumulators fit; else one warp-full of samples
+  if (L >= 32) cfg.group = 1;
+  else if (L >= 4) cfg.group = (64 + L - 1) / L < RT_ACC_LANES_MAX_GROUP ? (64 + L - 1) / L : RT_ACC_LANES_MAX_GROUP;
+  else cfg.group = 32 / L;
   cfg.rounds = (cfg.group * L + 31) / 32;
   cfg.n_tasks = (pm.n_pixels + cfg.group - 1) / cfg.group;
   // at most ~32 records per tree level are alive at any time, one level if N == 1
-  long long cap = a.num_of_rays == 1 ? 64 : 32ll * ((long long)a.max_depth + 1);
+  // stack capacity: every primary of the task may leave one level-1 record, and at most ~32 records
+  // per deeper tree level are alive at any time; with N == 1 a record is replaced
+  // by at most one record
+  const long long prims = (long long)cfg.rounds * 32;
+  long long cap = a.num_of_rays == 1 ? prims + 32 : prims + 32ll * (long long)a.max_depth;
   if (cap < 64) cap = 64;
   const int acc_mode = cfg.group == 1 ? ACC_REG : (cfg.group <= RT_ACC_LANES_MAX_GROUP ? ACC_LANES : ACC_SEG);
   size_t shape_bytes = (size_t)sc.n_pairs * 96 + (size_t)(sc.n_shapes - sc.n_spheres) * 48;
