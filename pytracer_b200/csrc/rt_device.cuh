@@ -232,7 +232,7 @@ template <bool UNROLL2 = true>
 RT_DEV void sweep_pairs(const float4* __restrict__ pairs, int base, int p0, int p1, const PackedRay& r,
                         int* cand, int& nc) {
   int p = p0;
-  if (!UNROLL2) {  // few spheres (e.g. demo.txt): one pair at a time keeps the register count low
+  if constexpr (!UNROLL2) {  // few spheres (e.g. demo.txt): one pair at a time keeps the register count low
 #pragma unroll 1
     for (; p < p1; ++p) {
       float a0, a1;
@@ -242,8 +242,7 @@ RT_DEV void sweep_pairs(const float4* __restrict__ pairs, int base, int p0, int 
         if (a1 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = 2 * p + 1; ++nc; }
       }
     }
-    return;
-  }
+  } else {
   for (; p + 2 <= p1; p += 2) {
     const float4* q = pairs + 6 * (p - base);
     float a0, a1, b0, b1;
@@ -261,6 +260,53 @@ RT_DEV void sweep_pairs(const float4* __restrict__ pairs, int base, int p0, int 
     upk2(pair_qdelta(pairs + 6 * (p - base), r), a0, a1);
     if (a0 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = 2 * p; ++nc; }
     if (a1 > 0.0f) { cand[nc & (RT_CAND_CAP - 1)] = 2 * p + 1; ++nc; }
+  }
+  }
+}
+
+// Two rays against the same pair data: the six LDS.128 of a pair feed 60 packed FMAs instead of 30,
+// which halves the shared-memory wavefronts per FMA (broadcast LDS.128 = 2 wavefronts; at one ray per
+// thread the shared-memory pipe runs at 80 % of the FMA pipe's pace and throttles it).
+RT_DEV void pair_qdelta2(const float4* __restrict__ q, const PackedRay& r0, const PackedRay& r1, f32x2& qd0, f32x2& qd1) {
+  const float4 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3], v4 = q[4], v5 = q[5];
+  const f32x2 m00 = pk2(v0.x, v0.y), m01 = pk2(v0.z, v0.w), m02 = pk2(v1.x, v1.y), m03 = pk2(v1.z, v1.w);
+  const f32x2 m10 = pk2(v2.x, v2.y), m11 = pk2(v2.z, v2.w), m12 = pk2(v3.x, v3.y), m13 = pk2(v3.z, v3.w);
+  const f32x2 m20 = pk2(v4.x, v4.y), m21 = pk2(v4.z, v4.w), m22 = pk2(v5.x, v5.y), m23 = pk2(v5.z, v5.w);
+#define RT_QD(r, out)                                                                  \
+  {                                                                                    \
+    const f32x2 px = fma2(m00, r.ox, fma2(m01, r.oy, fma2(m02, r.oz, m03)));           \
+    const f32x2 py = fma2(m10, r.ox, fma2(m11, r.oy, fma2(m12, r.oz, m13)));           \
+    const f32x2 pz = fma2(m20, r.ox, fma2(m21, r.oy, fma2(m22, r.oz, m23)));           \
+    const f32x2 dx = fma2(m00, r.dx, fma2(m01, r.dy, mul2(m02, r.dz)));                \
+    const f32x2 dy = fma2(m10, r.dx, fma2(m11, r.dy, mul2(m12, r.dz)));                \
+    const f32x2 dz = fma2(m20, r.dx, fma2(m21, r.dy, mul2(m22, r.dz)));                \
+    const f32x2 a = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));                          \
+    const f32x2 hb = fma2(px, dx, fma2(py, dy, mul2(pz, dz)));                         \
+    const f32x2 c = fma2(px, px, fma2(py, py, fma2(pz, pz, pk2(-1.0f, -1.0f))));       \
+    out = sub2(mul2(hb, hb), mul2(a, c));                                              \
+  }
+  RT_QD(r0, qd0)
+  RT_QD(r1, qd1)
+#undef RT_QD
+}
+
+RT_DEV void sweep_pairs2(const float4* __restrict__ pairs, int base, int p0, int p1, const Ray<float>& ray0,
+                         const Ray<float>& ray1, int* cand0, int& nc0, int* cand1, int& nc1) {
+  // the broadcast pairs are rebuilt here from the scalar rays: the compiler turns them into scalar
+  // (.F32) operands of FFMA2, so they cost no registers outside the loop
+  const PackedRay r0 = pack_ray(ray0), r1 = pack_ray(ray1);
+  for (int p = p0; p < p1; ++p) {
+    f32x2 q0, q1;
+    pair_qdelta2(pairs + 6 * (p - base), r0, r1, q0, q1);
+    float a0, a1, b0, b1;
+    upk2(q0, a0, a1);
+    upk2(q1, b0, b1);
+    if (fmaxf(fmaxf(a0, a1), fmaxf(b0, b1)) > 0.0f) {
+      if (a0 > 0.0f) { cand0[nc0 & (RT_CAND_CAP - 1)] = 2 * p; ++nc0; }
+      if (a1 > 0.0f) { cand0[nc0 & (RT_CAND_CAP - 1)] = 2 * p + 1; ++nc0; }
+      if (b0 > 0.0f) { cand1[nc1 & (RT_CAND_CAP - 1)] = 2 * p; ++nc1; }
+      if (b1 > 0.0f) { cand1[nc1 & (RT_CAND_CAP - 1)] = 2 * p + 1; ++nc1; }
+    }
   }
 }
 

@@ -274,7 +274,7 @@ k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
 }
 
 template <typename T>
-cudaError_t launch_resolve(const SceneView<T>& sc, const RenderArgs& a, cudaStream_t st, LaunchInfo* info) {
+cudaError_t launch_resolve_generic(const SceneView<T>& sc, const RenderArgs& a, cudaStream_t st, LaunchInfo* info) {
   PixelMap pm = make_pixel_map(a);
   if (pm.n_pixels == 0) return cudaSuccess;
   constexpr bool F32 = sizeof(T) == 4;

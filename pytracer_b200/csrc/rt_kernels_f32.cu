@@ -1,8 +1,11 @@
 // rt_kernels_f32.cu — float instantiations (multiply-add fusion allowed) + the warp-cooperative
 // path tracer, which exists in fp32 only.
 #include "rt_warp.cuh"
+#include "rt_resolve_f32.cuh"
 
-template cudaError_t launch_resolve<float>(const SceneView<float>&, const RenderArgs&, cudaStream_t, LaunchInfo*);
+template <> cudaError_t launch_resolve<float>(const SceneView<float>& sc, const RenderArgs& a, cudaStream_t st, LaunchInfo* info) {
+  return launch_resolve_f32(sc, a, st, info);
+}
 template cudaError_t launch_pt_mega<float>(const SceneView<float>&, const RenderArgs&, cudaStream_t, LaunchInfo*);
 template cudaError_t launch_probe<float>(const SceneView<float>&, const RenderArgs&, const ProbeArgs&, cudaStream_t);
 
