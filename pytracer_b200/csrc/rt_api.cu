@@ -161,7 +161,9 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
   UP(invm32, invm32) UP(m32, m32) UP(invm64, invm64) UP(m64, m64) UP(orig, orig) UP(material, mat)
   // fp32 scan array: sphere pairs element-interleaved (operands of the packed FFMA2 sweep), odd count
   // padded with an all-zero record (never crossed), then the plane records
-  s->n_pairs = (s->n_spheres + 1) / 2;
+  // an even pair count for real scenes (the warp sweep splits the list between half-warps); tiny scenes
+  // (demo.txt: one sphere) are not padded — every pair costs 30 FFMA2 per ray
+  s->n_pairs = s->n_spheres > 8 ? ((s->n_spheres + 3) / 4) * 2 : (s->n_spheres + 1) / 2;
   std::vector<float> packed((size_t)s->n_pairs * 24 + (size_t)(s->n_shapes - s->n_spheres) * 12, 0.0f);
   for (int i = 0; i < s->n_spheres; ++i)
     for (int k = 0; k < 12; ++k) packed[(size_t)(i / 2) * 24 + 2 * k + (i & 1)] = invm32[12 * (size_t)i + k];

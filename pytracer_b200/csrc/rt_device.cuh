@@ -310,6 +310,45 @@ RT_DEV void sweep_pairs2(const float4* __restrict__ pairs, int base, int p0, int
   }
 }
 
+// Warp-cooperative sweep for one ray per lane (the path tracer's layout).  A broadcast LDS.128 costs
+// two shared-memory wavefronts, one per half-warp, whatever the two halves read — so the halves read
+// DIFFERENT pairs: lanes 0-15 sweep the first half of the pair list, lanes 16-31 the second half, each
+// lane for its own ray and for the ray of its partner lane (lane ^ 16, fetched with six shuffles).  Same
+// FMA work per lane (two rays x half the pairs), half the shared-memory wavefronts per FMA.  After the
+// sweep the partner's candidates are handed back with shuffles and merged in ascending sphere order.
+// Must be called by all 32 lanes (idle lanes pass a zero ray: a = 0, delta = 0, never crossed);
+// n_pairs is even (rt_scene_create pads the pair list).
+RT_DEV void sweep_pairs_split(const float4* __restrict__ pairs, int n_pairs, const Ray<float>& mine, int* cand, int& nc) {
+  const unsigned FULL = 0xffffffffu;
+  const bool hi = (threadIdx.x & 16) != 0;
+  Ray<float> other;
+  other.o.x = __shfl_xor_sync(FULL, mine.o.x, 16); other.o.y = __shfl_xor_sync(FULL, mine.o.y, 16);
+  other.o.z = __shfl_xor_sync(FULL, mine.o.z, 16); other.d.x = __shfl_xor_sync(FULL, mine.d.x, 16);
+  other.d.y = __shfl_xor_sync(FULL, mine.d.y, 16); other.d.z = __shfl_xor_sync(FULL, mine.d.z, 16);
+  const int half = n_pairs >> 1;
+  const int first = hi ? half : 0;
+  int theirs[RT_CAND_CAP];
+  int n_mine = 0, n_theirs = 0;
+  sweep_pairs2(pairs, 0, first, first + half, mine, other, cand, n_mine, theirs, n_theirs);
+  // hand the partner's candidates back; the low half's spheres come first in the merged list
+  const int n_recv = __shfl_xor_sync(FULL, n_theirs, 16);
+  int merged[RT_CAND_CAP];
+  const int total = n_mine + n_recv;
+  const int at_recv = hi ? 0 : n_mine, at_mine = hi ? n_recv : 0;
+#pragma unroll
+  for (int j = 0; j < RT_CAND_CAP; ++j) {
+    const int v = __shfl_xor_sync(FULL, theirs[j], 16);
+    if (j < n_recv && at_recv + j < RT_CAND_CAP) merged[at_recv + j] = v;
+  }
+  if (n_mine <= RT_CAND_CAP && n_recv <= RT_CAND_CAP && total <= RT_CAND_CAP) {
+    for (int j = 0; j < n_mine; ++j) merged[at_mine + j] = cand[j];
+    for (int j = 0; j < total; ++j) cand[j] = merged[j];
+    nc = total;
+  } else {
+    nc = RT_CAND_CAP + 1;  // too many crossed spheres for the lists: resolve_candidates does a plain pass
+  }
+}
+
 // Exact roots for the crossed spheres only, from the plain [n][12] array in global memory (a few per
 // ray: L1/L2 hits).  Ascending index + strict '<' keeps the first shape on ties (world.py:62).
 //
@@ -415,6 +454,18 @@ template <typename T>
 RT_DEV void closest_all(const SceneView<T>& sc, const ScanSrc<T>& src, const Ray<T>& r, T& best_t, int& best, int origin = -1) {
   scan_closest<T>(src.xf, 0, sc.n_shapes, sc.n_spheres, sc.orig, r, best_t, best);
 }
+// all 32 lanes together (see sweep_pairs_split); `live` = this lane really has a ray
+RT_DEV void closest_all_warp(const SceneView<float>& sc, const ScanSrc<float>& src, const Ray<float>& r, bool live,
+                             float& best_t, int& best, int origin) {
+  int cand[RT_CAND_CAP];
+  int nc = 0;
+  if (sc.n_pairs > 0) sweep_pairs_split(src.pairs, sc.n_pairs, r, cand, nc);
+  if (live) {
+    resolve_candidates(sc.invm, sc.n_spheres, cand, nc, r, best_t, best, origin);
+    scan_plane_block(src.planes, sc.n_spheres, sc.n_shapes - sc.n_spheres, sc.orig, r, best_t, best, origin);
+  }
+}
+
 template <bool UNROLL2>
 RT_DEV void closest_all_f32(const SceneView<float>& sc, const ScanSrc<float>& src, const Ray<float>& r,
                             float& best_t, int& best, int origin = -1) {

@@ -19,6 +19,9 @@
 #include "rt_kernels.cuh"
 
 #define RT_WARP_MAX_THREADS 256
+#ifndef RT_WARP_SPLIT
+#define RT_WARP_SPLIT 1
+#endif
 
 
 struct __align__(16) ScatterRec {
@@ -203,11 +206,16 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
         V3<float> contrib = mk3<float>(0.f, 0.f, 0.f);
         bool push = false;
         ScatterRec out;
+        float best_t = Num<float>::inf();
+        int best = -1;
+        if (!SMALL && RT_WARP_SPLIT) {  // large scenes: the whole warp sweeps together, half-warps on different pairs
+          if (!active) { ray.o = mk3<float>(0.f, 0.f, 0.f); ray.d = mk3<float>(0.f, 0.f, 0.f); ray.tmin = 0.f; ray.tmax = 0.f; }
+          closest_all_warp(sc, src, ray, active, best_t, best, origin);
+        }
         if (active) {
           Hit<float> h;
-          float best_t = Num<float>::inf();
-          int best = -1;
-          closest_all_f32<!SMALL>(sc, src, ray, best_t, best, origin);
+          if (SMALL) closest_all_f32<false>(sc, src, ray, best_t, best, origin);
+          else if (!RT_WARP_SPLIT) closest_all_f32<true>(sc, src, ray, best_t, best, origin);
           const bool found = best >= 0;
           if (found) finish_hit<float>(sc, ray, best_t, best, h);
           ++n_rays;
@@ -348,14 +356,19 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   if (a.max_depth >= 1023) { *why_not = "max_depth >= 1023 is not supported by the warp variant (use mega)"; return cudaErrorInvalidValue; }
   WarpCfg cfg;
   cfg.per_pixel = L;
-  // pixels per task: one when a pixel alone fills the warp; up to 8 (>= 64 samples per task) while
-  // lane-private accumulators fit; else one warp-full of samples
+  // Samples per task.  Scenes whose shape block is tiny (demo.txt) take tasks of >= 64 samples (fewer
+  // partially filled iterations per sample); scenes that fill shared memory with shapes keep one
+  // warp-full per task so that two CTAs still fit an SM.
+  size_t shape_bytes = (size_t)sc.n_pairs * 96 + (size_t)(sc.n_shapes - sc.n_spheres) * 48;
+  const bool shapes_smem = shape_bytes > 0 && shape_bytes <= 64 * 1024;
+  const bool small = sc.n_spheres <= 8 && shapes_smem;
+  const int want = small ? 64 : 32;
   if (L >= 32) cfg.group = 1;
-  else if (L >= 4) cfg.group = (64 + L - 1) / L < RT_ACC_LANES_MAX_GROUP ? (64 + L - 1) / L : RT_ACC_LANES_MAX_GROUP;
+  else if (L >= 4) cfg.group = (want + L - 1) / L < RT_ACC_LANES_MAX_GROUP ? (want + L - 1) / L : RT_ACC_LANES_MAX_GROUP;
   else cfg.group = 32 / L;
+  if (cfg.group * L > 32 && !small) cfg.group = 32 / L > 0 ? 32 / L : 1;
   cfg.rounds = (cfg.group * L + 31) / 32;
   cfg.n_tasks = (pm.n_pixels + cfg.group - 1) / cfg.group;
-  // at most ~32 records per tree level are alive at any time, one level if N == 1
   // stack capacity: every primary of the task may leave one level-1 record, and at most ~32 records
   // per deeper tree level are alive at any time; with N == 1 a record is replaced
   // by at most one record
@@ -363,8 +376,6 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   long long cap = a.num_of_rays == 1 ? prims + 32 : prims + 32ll * (long long)a.max_depth;
   if (cap < 64) cap = 64;
   const int acc_mode = cfg.group == 1 ? ACC_REG : (cfg.group <= RT_ACC_LANES_MAX_GROUP ? ACC_LANES : ACC_SEG);
-  size_t shape_bytes = (size_t)sc.n_pairs * 96 + (size_t)(sc.n_shapes - sc.n_spheres) * 48;
-  const bool shapes_smem = shape_bytes > 0 && shape_bytes <= 64 * 1024;
   cfg.shape_bytes = shapes_smem ? (int)((shape_bytes + 15) / 16 * 16) : 0;
   const size_t limit = 200 * 1024;
   int warps = RT_WARP_MAX_THREADS / 32;
@@ -381,7 +392,6 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   cfg.per_warp_bytes = (int)per_warp;
 
   void (*kern)(const SceneView<float>, const RenderArgs, const WarpCfg);
-  const bool small = sc.n_spheres <= 8 && shapes_smem;
 #define RT_PICK(ACCM)                                                                   \
   (small ? k_pt_warp<true, ACCM, true> : (shapes_smem ? k_pt_warp<true, ACCM, false> : k_pt_warp<false, ACCM, false>))
   if (acc_mode == ACC_REG) kern = RT_PICK(ACC_REG);
