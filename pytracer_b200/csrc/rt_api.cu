@@ -32,9 +32,28 @@ static int fail(int code, const char* fmt, ...) {
       return fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+// Per-device scratch shared by every scene of the process (one caller thread, see rt_api.h): counters,
+// timing events and the staging buffers of the host-buffer entry points.  Created on first use and kept
+// for the life of the process, so that creating / destroying a scene costs one allocation and one copy.
+struct Workspace {
+  unsigned long long* counters = nullptr;       // device, CNT_SLOTS
+  unsigned long long* counters_host = nullptr;  // pinned
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, t0 = nullptr, t1 = nullptr;
+  uint64_t* replay = nullptr;
+  size_t replay_cap = 0;
+  void* image = nullptr;  // scratch image for the host-buffer entry point
+  size_t image_cap = 0;
+  int32_t* hit = nullptr;
+  size_t hit_cap = 0;
+  void* probe_buf = nullptr;
+  size_t probe_cap = 0;
+  int sm_count = 0;
+};
+
 struct rt_scene {
   int device = 0, sm_count = 0;
   int n_shapes = 0, n_spheres = 0, n_materials = 0, n_pigments = 0, n_lights = 0;
+  void* arena = nullptr;  // ONE device allocation holding every table below
   float *invm32 = nullptr, *m32 = nullptr, *packed32 = nullptr;
   int n_pairs = 0;
   double *invm64 = nullptr, *m64 = nullptr;
@@ -45,21 +64,31 @@ struct rt_scene {
   double* texels64 = nullptr;
   std::vector<cudaArray_t> arrays;
   std::vector<cudaTextureObject_t> textures;
-  unsigned long long* counters = nullptr;       // device, CNT_SLOTS
-  unsigned long long* counters_host = nullptr;  // pinned
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  uint64_t* replay = nullptr;
-  size_t replay_cap = 0;
-  void* image = nullptr;  // scratch image for the host-buffer entry point
-  size_t image_cap = 0;
-  int32_t* hit = nullptr;
-  size_t hit_cap = 0;
-  void* probe_buf = nullptr;
-  size_t probe_cap = 0;
+  Workspace* ws = nullptr;
   LaunchInfo last_info = {0, 0};
   int last_precision = 0;
   bool pending = false;
 };
+
+static int get_workspace(int device, Workspace** out) {
+  static Workspace* table[64] = {nullptr};
+  if (device < 0 || device >= 64) return fail(RT_ERR_INVALID, "device index %d", device);
+  if (!table[device]) {
+    Workspace* w = new Workspace();
+    // (cudaGetDeviceProperties takes tens of milliseconds; one attribute query, once per device)
+    cudaError_t e = cudaDeviceGetAttribute(&w->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&w->counters, CNT_SLOTS * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&w->counters_host, CNT_SLOTS * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaEventCreate(&w->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&w->t0);
+    if (e == cudaSuccess) e = cudaEventCreate(&w->t1);
+    if (e != cudaSuccess) { delete w; return fail(RT_ERR_CUDA, "workspace: %s", cudaGetErrorString(e)); }
+    table[device] = w;
+  }
+  *out = table[device];
+  return RT_OK;
+}
 
 extern "C" int rt_api_version(void) { return RT_API_VERSION; }
 
@@ -98,25 +127,23 @@ template <> SceneView<double> view_of<double>(const rt_scene* s) {
   return v;
 }
 
-template <typename T> static int upload(T** dst, const std::vector<T>& src) {
-  size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
-  CU(cudaMalloc((void**)dst, bytes));
-  if (!src.empty()) CU(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
-  return RT_OK;
-}
+// Host-side staging of the scene arena: tables are appended 256-byte aligned, uploaded with one copy.
+struct Arena {
+  std::vector<unsigned char> host;
+  template <typename T> size_t add(const std::vector<T>& v) {
+    size_t off = (host.size() + 255) / 256 * 256;
+    host.resize(off + std::max<size_t>(v.size(), 1) * sizeof(T), 0);
+    if (!v.empty()) memcpy(host.data() + off, v.data(), v.size() * sizeof(T));
+    return off;
+  }
+};
 
 extern "C" void rt_scene_destroy(rt_scene* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   for (auto t : s->textures) cudaDestroyTextureObject(t);
   for (auto a : s->arrays) cudaFreeArray(a);
-  cudaFree(s->invm32); cudaFree(s->m32); cudaFree(s->packed32); cudaFree(s->invm64); cudaFree(s->m64);
-  cudaFree(s->orig); cudaFree(s->material); cudaFree(s->materials); cudaFree(s->pigments);
-  cudaFree(s->lights); cudaFree(s->texels64); cudaFree(s->counters); cudaFree(s->replay);
-  cudaFree(s->image); cudaFree(s->hit); cudaFree(s->probe_buf);
-  if (s->counters_host) cudaFreeHost(s->counters_host);
-  if (s->ev0) cudaEventDestroy(s->ev0);
-  if (s->ev1) cudaEventDestroy(s->ev1);
+  cudaFree(s->arena);
   delete s;
 }
 
@@ -128,9 +155,6 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
   rt_scene* s = new rt_scene();
   *out = nullptr;
   cudaGetDevice(&s->device);
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, s->device) != cudaSuccess) { delete s; return fail(RT_ERR_CUDA, "cudaGetDeviceProperties failed"); }
-  s->sm_count = prop.multiProcessorCount;
   s->n_shapes = d->n_shapes; s->n_materials = d->n_materials; s->n_pigments = d->n_pigments; s->n_lights = d->n_lights;
 
   // ---- shapes, sorted spheres first / planes after, World.shapes order kept inside each group
@@ -157,7 +181,11 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
     }
   }
   int rc;
-#define UP(field, vec) if ((rc = upload(&s->field, vec)) != RT_OK) { rt_scene_destroy(s); return rc; }
+  if ((rc = get_workspace(s->device, &s->ws)) != RT_OK) { delete s; return rc; }
+  s->sm_count = s->ws->sm_count;
+  Arena arena;
+  std::vector<std::pair<void**, size_t>> fixups;  // (pointer field, offset in the arena)
+#define UP(field, vec) fixups.push_back({(void**)&s->field, arena.add(vec)});
   UP(invm32, invm32) UP(m32, m32) UP(invm64, invm64) UP(m64, m64) UP(orig, orig) UP(material, mat)
   // fp32 scan array: sphere pairs element-interleaved (operands of the packed FFMA2 sweep), odd count
   // padded with an all-zero record (never crossed), then the plane records
@@ -174,7 +202,8 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
   // ---- textures: fp64 copy for the fp64 path, float4 CUDA arrays behind texture objects for fp32
   std::vector<double> tex64;
   if (d->n_texels > 0) tex64.assign(d->texels, d->texels + 3 * (size_t)d->n_texels);
-  UP(texels64, tex64)
+  const size_t tex64_off = arena.add(tex64);
+  fixups.push_back({(void**)&s->texels64, tex64_off});
   std::vector<DevPigment> pigs(d->n_pigments);
   for (int i = 0; i < d->n_pigments; ++i) {
     const rt_pigment& p = d->pigments[i];
@@ -191,7 +220,7 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
         rt_scene_destroy(s);
         return fail(RT_ERR_INVALID, "pigment %d: texture window outside the texel buffer", i);
       }
-      q.texels64 = s->texels64 + 3 * (size_t)p.tex_offset;
+      q.texels64 = reinterpret_cast<const double*>(3 * (size_t)p.tex_offset * sizeof(double));  // + arena base, patched below
       std::vector<float4> texels((size_t)p.tex_width * p.tex_height);
       const double* src = d->texels + 3 * (size_t)p.tex_offset;
       for (size_t t = 0; t < texels.size(); ++t)
@@ -229,7 +258,7 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
       return fail(RT_ERR_INVALID, "pigment %d: unknown kind %d", i, p.kind);
     }
   }
-  UP(pigments, pigs)
+  // materials and lights first, pigments last: their fp64 texel pointers need the arena's device address
   std::vector<DevMaterial> mats(d->n_materials);
   for (int i = 0; i < d->n_materials; ++i) {
     const rt_material& m = d->materials[i];
@@ -250,12 +279,18 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
     lights[i].radius = d->lights[i].linear_radius;
   }
   UP(lights, lights)
+  const size_t pig_off = arena.add(pigs);
+  fixups.push_back({(void**)&s->pigments, pig_off});
 #undef UP
-  cudaError_t e = cudaMalloc((void**)&s->counters, CNT_SLOTS * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->counters_host, CNT_SLOTS * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
-  if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
-  if (e != cudaSuccess) { rt_scene_destroy(s); return fail(RT_ERR_CUDA, "scene scratch: %s", cudaGetErrorString(e)); }
+  cudaError_t e = cudaMalloc(&s->arena, arena.host.size());
+  if (e != cudaSuccess) { rt_scene_destroy(s); return fail(RT_ERR_CUDA, "scene arena (%zu bytes): %s", arena.host.size(), cudaGetErrorString(e)); }
+  for (auto& f : fixups) *f.first = (unsigned char*)s->arena + f.second;
+  DevPigment* staged = reinterpret_cast<DevPigment*>(arena.host.data() + pig_off);
+  for (int i = 0; i < d->n_pigments; ++i)
+    if (staged[i].kind == RT_PIGMENT_IMAGE)
+      staged[i].texels64 = reinterpret_cast<const double*>((unsigned char*)s->texels64 + (size_t)staged[i].texels64);
+  e = cudaMemcpy(s->arena, arena.host.data(), arena.host.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { rt_scene_destroy(s); return fail(RT_ERR_CUDA, "scene upload: %s", cudaGetErrorString(e)); }
   *out = s;
   return RT_OK;
 }
@@ -291,7 +326,7 @@ static int fill_args(const rt_scene* s, const rt_render_params* p, RenderArgs* a
   a->part_rank = p->part_rank; a->part_count = p->part_count > 1 ? p->part_count : 1;
   a->out_f64 = p->out_f64 ? 1 : 0;
   a->hit_mode = p->hit_mode;
-  a->counters = s->counters;
+  a->counters = s->ws->counters;
   build_jump_table(p->aa_inc, &a->jump);
   return RT_OK;
 }
@@ -327,13 +362,13 @@ extern "C" int rt_render_device(rt_scene* s, const rt_render_params* p, void* d_
       if (!p->replay_states) return fail(RT_ERR_INVALID, "RT_RNG_REPLAY without replay_states");
       long long S2 = p->samples_per_side > 0 ? (long long)p->samples_per_side * p->samples_per_side : 1;
       size_t bytes = (size_t)p->width * p->height * S2 * sizeof(uint64_t);
-      if ((rc = ensure((void**)&s->replay, &s->replay_cap, bytes)) != RT_OK) return rc;
-      CU(cudaMemcpyAsync(s->replay, p->replay_states, bytes, cudaMemcpyHostToDevice, st));
-      a.replay = s->replay;
+      if ((rc = ensure((void**)&s->ws->replay, &s->ws->replay_cap, bytes)) != RT_OK) return rc;
+      CU(cudaMemcpyAsync(s->ws->replay, p->replay_states, bytes, cudaMemcpyHostToDevice, st));
+      a.replay = s->ws->replay;
     }
   }
   size_t px = (size_t)p->width * p->height;
-  CU(cudaMemsetAsync(s->counters, 0, CNT_SLOTS * sizeof(unsigned long long), st));
+  CU(cudaMemsetAsync(s->ws->counters, 0, CNT_SLOTS * sizeof(unsigned long long), st));
   // rows this rank does not own stay zero, so that a sum over ranks is the image
   const bool partial_rows = a.part_mode == RT_PART_ROWS;
   long long S2 = p->samples_per_side > 0 ? (long long)p->samples_per_side * p->samples_per_side : 1;
@@ -344,7 +379,7 @@ extern "C" int rt_render_device(rt_scene* s, const rt_render_params* p, void* d_
   }
   s->last_info = {0, 0};
   s->last_precision = precision;
-  CU(cudaEventRecord(s->ev0, st));
+  CU(cudaEventRecord(s->ws->ev0, st));
   cudaError_t e = cudaSuccess;
   const char* why = nullptr;
   if (!pt) {
@@ -358,8 +393,8 @@ extern "C" int rt_render_device(rt_scene* s, const rt_render_params* p, void* d_
     e = launch_pt_warp(view_of<float>(s), a, st, s->sm_count, &s->last_info, &why);
   }
   if (e != cudaSuccess) return fail(why ? RT_ERR_INVALID : RT_ERR_CUDA, "render launch: %s", why ? why : cudaGetErrorString(e));
-  CU(cudaEventRecord(s->ev1, st));
-  CU(cudaMemcpyAsync(s->counters_host, s->counters, CNT_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(s->ws->ev1, st));
+  CU(cudaMemcpyAsync(s->ws->counters_host, s->ws->counters, CNT_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   s->pending = true;
   return RT_OK;
 }
@@ -371,12 +406,12 @@ extern "C" int rt_render_finish(rt_scene* s, void* stream, rt_stats* stats) {
   if (stats) {
     memset(stats, 0, sizeof(*stats));
     if (s->pending) {
-      stats->rays_closest = s->counters_host[CNT_CLOSEST];
-      stats->rays_shadow = s->counters_host[CNT_SHADOW];
-      stats->samples = s->counters_host[CNT_SAMPLES];
-      stats->overflow = (int32_t)s->counters_host[CNT_OVERFLOW];
+      stats->rays_closest = s->ws->counters_host[CNT_CLOSEST];
+      stats->rays_shadow = s->ws->counters_host[CNT_SHADOW];
+      stats->samples = s->ws->counters_host[CNT_SAMPLES];
+      stats->overflow = (int32_t)s->ws->counters_host[CNT_OVERFLOW];
       float ms = 0.f;
-      CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+      CU(cudaEventElapsedTime(&ms, s->ws->ev0, s->ws->ev1));
       stats->kernel_ms = ms;
       stats->total_ms = ms;
       stats->variant_used = s->last_info.variant;
@@ -384,7 +419,7 @@ extern "C" int rt_render_finish(rt_scene* s, void* stream, rt_stats* stats) {
       stats->n_launches = s->last_info.n_launches;
     }
   }
-  bool ovf = s->pending && s->counters_host[CNT_OVERFLOW] != 0;
+  bool ovf = s->pending && s->ws->counters_host[CNT_OVERFLOW] != 0;
   s->pending = false;
   if (ovf) return fail(RT_ERR_OVERFLOW, "a warp work stack overflowed; the image is invalid");
   return RT_OK;
@@ -397,16 +432,14 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, void* out_rgb, 
   size_t px = (size_t)p->width * p->height;
   size_t bytes = px * 3 * (p->out_f64 ? sizeof(double) : sizeof(float));
   int rc;
-  if ((rc = ensure(&s->image, &s->image_cap, bytes)) != RT_OK) return rc;
-  if (out_hit && (rc = ensure((void**)&s->hit, &s->hit_cap, px * sizeof(int32_t))) != RT_OK) return rc;
-  cudaEvent_t t0, t1;
-  CU(cudaEventCreate(&t0));
-  CU(cudaEventCreate(&t1));
+  if ((rc = ensure(&s->ws->image, &s->ws->image_cap, bytes)) != RT_OK) return rc;
+  if (out_hit && (rc = ensure((void**)&s->ws->hit, &s->ws->hit_cap, px * sizeof(int32_t))) != RT_OK) return rc;
+  cudaEvent_t t0 = s->ws->t0, t1 = s->ws->t1;
   CU(cudaEventRecord(t0, 0));
-  rc = rt_render_device(s, p, s->image, out_hit ? s->hit : nullptr, nullptr);
+  rc = rt_render_device(s, p, s->ws->image, out_hit ? s->ws->hit : nullptr, nullptr);
   if (rc == RT_OK) {
-    cudaError_t e = cudaMemcpyAsync(out_rgb, s->image, bytes, cudaMemcpyDeviceToHost, 0);
-    if (e == cudaSuccess && out_hit) e = cudaMemcpyAsync(out_hit, s->hit, px * sizeof(int32_t), cudaMemcpyDeviceToHost, 0);
+    cudaError_t e = cudaMemcpyAsync(out_rgb, s->ws->image, bytes, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess && out_hit) e = cudaMemcpyAsync(out_hit, s->ws->hit, px * sizeof(int32_t), cudaMemcpyDeviceToHost, 0);
     if (e == cudaSuccess) e = cudaEventRecord(t1, 0);
     if (e != cudaSuccess) rc = fail(RT_ERR_CUDA, "image copy: %s", cudaGetErrorString(e));
   }
@@ -415,8 +448,6 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, void* out_rgb, 
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) stats->total_ms = ms;
   }
-  cudaEventDestroy(t0);
-  cudaEventDestroy(t1);
   return rc;
 }
 
@@ -445,12 +476,12 @@ static int run_probe(rt_scene* s, int precision, const rt_render_params* p, int 
   auto align = [](size_t x) { return (x + 255) / 256 * 256; };
   size_t off_in = 0, off_depth = align(in_bytes), off_pcg = off_depth + align(depth ? n * sizeof(int32_t) : 0);
   size_t off_out = off_pcg + 256, total = off_out + align(out_bytes);
-  if ((rc = ensure(&s->probe_buf, &s->probe_cap, total)) != RT_OK) return rc;
-  unsigned char* base = (unsigned char*)s->probe_buf;
+  if ((rc = ensure(&s->ws->probe_buf, &s->ws->probe_cap, total)) != RT_OK) return rc;
+  unsigned char* base = (unsigned char*)s->ws->probe_buf;
   if (in_bytes) CU(cudaMemcpy(base + off_in, in, in_bytes, cudaMemcpyHostToDevice));
   if (depth) CU(cudaMemcpy(base + off_depth, depth, n * sizeof(int32_t), cudaMemcpyHostToDevice));
   if (pcg) CU(cudaMemcpy(base + off_pcg, pcg, 2 * sizeof(uint64_t), cudaMemcpyHostToDevice));
-  CU(cudaMemset(s->counters, 0, CNT_SLOTS * sizeof(unsigned long long)));
+  CU(cudaMemset(s->ws->counters, 0, CNT_SLOTS * sizeof(unsigned long long)));
   ProbeArgs pa;
   memset(&pa, 0, sizeof(pa));
   pa.what = what; pa.n = n; pa.aux = aux;
