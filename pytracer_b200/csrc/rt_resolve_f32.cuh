@@ -3,8 +3,12 @@
 // pixel, strata in the reference's order, shapes staged through shared memory by the block — but the
 // strata of a pixel are traced TWO AT A TIME against each staged sphere pair: six broadcast LDS.128 feed
 // 60 packed FMAs (FFMA2) instead of 30, so the shared-memory pipe stops throttling the FMA pipe.
+// Scenes larger than 96 KB of pairs are swept in 48 KB chunks through a DOUBLE BUFFER filled by the TMA
+// engine (cp.async.bulk + mbarrier, rt_tma.cuh): one thread posts the copy of chunk c+1, everybody sweeps
+// chunk c; a block barrier per chunk only guards the buffer about to be overwritten.
 #pragma once
 #include "rt_kernels.cuh"
+#include "rt_tma.cuh"
 
 struct ResolveSample {
   Ray<float> ray;
@@ -50,9 +54,25 @@ k_resolve_f32(const __grid_constant__ SceneView<float> sc, const __grid_constant
   const long long pix = (long long)row * a.width + col;
   const int S2 = a.S > 0 ? a.S * a.S : 1;
 
+  // double buffer + two mbarriers behind it (chunked scenes); one buffer when everything fits
+  float4* buf[2] = {sh_pairs, sh_pairs + (single ? 0 : 6 * (size_t)chunk)};
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sh_pairs + 6 * (size_t)chunk * (single ? 1 : 2));
+  uint32_t parity[2] = {0u, 0u};
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
   if (planes_smem) stage_bytes(sh_planes, planes_g, (size_t)n_planes * 48);
-  if (single) stage_bytes(sh_pairs, sc.packed, (size_t)sc.n_pairs * 96);
   __syncthreads();
+  if (single && sc.n_pairs > 0) {  // the whole pair list, once, by the copy engine
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(&bars[0], (uint32_t)sc.n_pairs * 96u);
+      tma_load_1d(buf[0], sc.packed, (uint32_t)sc.n_pairs * 96u, &bars[0]);
+    }
+    mbar_wait(&bars[0], 0);
+    parity[0] = 1;
+  }
 
   Pcg aa;
   aa.inc = a.aa_inc;
@@ -61,21 +81,34 @@ k_resolve_f32(const __grid_constant__ SceneView<float> sc, const __grid_constant
   int last_hit = -1;
   unsigned int n_closest = 0, n_shadow = 0, n_samples = 0;
   const V3<float> background = load3<float>(a.background);
+  const int n_chunks = single ? 1 : (sc.n_pairs + chunk - 1) / chunk;
 
-  // one sweep of all sphere pairs for one or two rays (block-uniform control flow: `two`, `go`)
+  auto post_chunk = [&](int c) {  // thread 0: start the bulk copy of chunk c into buffer c & 1
+    const int b0 = c * chunk, b1 = min(b0 + chunk, sc.n_pairs);
+    const uint32_t bytes = (uint32_t)(b1 - b0) * 96u;
+    mbar_arrive_expect_tx(&bars[c & 1], bytes);
+    tma_load_1d(buf[c & 1], sc.packed + 24 * (size_t)b0, bytes, &bars[c & 1]);
+  };
+
+  // one sweep of all sphere pairs for one or two rays (block-uniform control flow)
   auto sweep = [&](bool two, bool on0, bool on1, const Ray<float>& r0, const Ray<float>& r1, int* c0, int& n0, int* c1, int& n1) {
     if (single) {
-      if (two) { if (on0 || on1) sweep_pairs2(sh_pairs, 0, 0, sc.n_pairs, r0, r1, c0, n0, c1, n1); }
-      else if (on0) sweep_pairs<true>(sh_pairs, 0, 0, sc.n_pairs, pack_ray(r0), c0, n0);
-    } else {
-      for (int b0 = 0; b0 < sc.n_pairs; b0 += chunk) {
-        const int b1 = min(b0 + chunk, sc.n_pairs);
-        __syncthreads();
-        stage_bytes(sh_pairs, sc.packed + 24 * (size_t)b0, (size_t)(b1 - b0) * 96);
-        __syncthreads();
-        if (two) { if (on0 || on1) sweep_pairs2(sh_pairs, b0, b0, b1, r0, r1, c0, n0, c1, n1); }
-        else if (on0) sweep_pairs<true>(sh_pairs, b0, b0, b1, pack_ray(r0), c0, n0);
+      if (two) { if (on0 || on1) sweep_pairs2(buf[0], 0, 0, sc.n_pairs, r0, r1, c0, n0, c1, n1); }
+      else if (on0) sweep_pairs<true>(buf[0], 0, 0, sc.n_pairs, pack_ray(r0), c0, n0);
+      return;
+    }
+    __syncthreads();  // the previous sweep is done with both buffers
+    if (threadIdx.x == 0) post_chunk(0);
+    for (int c = 0; c < n_chunks; ++c) {
+      const int b0 = c * chunk, b1 = min(b0 + chunk, sc.n_pairs);
+      if (c + 1 < n_chunks) {
+        if (c >= 1) __syncthreads();  // chunk c - 1, which lived in the buffer about to be refilled, is consumed
+        if (threadIdx.x == 0) post_chunk(c + 1);
       }
+      mbar_wait(&bars[c & 1], parity[c & 1]);
+      parity[c & 1] ^= 1u;
+      if (two) { if (on0 || on1) sweep_pairs2(buf[c & 1], b0, b0, b1, r0, r1, c0, n0, c1, n1); }
+      else if (on0) sweep_pairs<true>(buf[c & 1], b0, b0, b1, pack_ray(r0), c0, n0);
     }
   };
 
@@ -142,13 +175,14 @@ k_resolve_f32(const __grid_constant__ SceneView<float> sc, const __grid_constant
 inline cudaError_t launch_resolve_f32(const SceneView<float>& sc, const RenderArgs& a, cudaStream_t st, LaunchInfo* info) {
   PixelMap pm = make_pixel_map(a);
   if (pm.n_pixels == 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(k_resolve_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RT_SMEM_SHAPE_BYTES + 16 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(k_resolve_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RT_SMEM_SHAPE_BYTES + 17 * 1024);
   if (e != cudaSuccess) return e;
   const int n_planes = sc.n_shapes - sc.n_spheres;
   const size_t planes_bytes = n_planes <= RT_PLANES_SMEM_MAX ? (size_t)n_planes * 48 : 0;
   // everything in one chunk while it fits 96 KB of shared memory, else 48 KB chunks (512 pairs)
   int chunk = (size_t)sc.n_pairs * 96 <= 2 * RT_SMEM_SHAPE_BYTES ? (sc.n_pairs > 0 ? sc.n_pairs : 1) : RT_SMEM_SHAPE_BYTES / 96;
-  size_t smem = planes_bytes + (size_t)chunk * 96;
+  const bool single = sc.n_pairs <= chunk;
+  size_t smem = planes_bytes + (size_t)chunk * 96 * (single ? 1 : 2) + 16;  // + two mbarriers
   long long blocks = (pm.n_pixels + RT_RESOLVE_THREADS - 1) / RT_RESOLVE_THREADS;
   k_resolve_f32<<<(unsigned)blocks, RT_RESOLVE_THREADS, smem, st>>>(sc, a, chunk);
   if (info) { info->n_launches += 1; info->variant = 0; }
