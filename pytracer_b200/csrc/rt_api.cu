@@ -116,6 +116,7 @@ template <> SceneView<float> view_of<float>(const rt_scene* s) {
   v.materials = s->materials; v.pigments = s->pigments; v.lights = s->lights;
   v.n_shapes = s->n_shapes; v.n_spheres = s->n_spheres; v.n_lights = s->n_lights;
   v.packed = s->packed32; v.n_pairs = s->n_pairs; v._pad = 0;
+  v.n_materials = s->n_materials; v.n_pigments = s->n_pigments;
   return v;
 }
 template <> SceneView<double> view_of<double>(const rt_scene* s) {
@@ -124,6 +125,7 @@ template <> SceneView<double> view_of<double>(const rt_scene* s) {
   v.materials = s->materials; v.pigments = s->pigments; v.lights = s->lights;
   v.n_shapes = s->n_shapes; v.n_spheres = s->n_spheres; v.n_lights = s->n_lights;
   v.packed = nullptr; v.n_pairs = 0; v._pad = 0;
+  v.n_materials = s->n_materials; v.n_pigments = s->n_pigments;
   return v;
 }
 
@@ -268,8 +270,16 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
       return fail(RT_ERR_INVALID, "material %d: bad BRDF kind or pigment index", i);
     }
     mats[i].brdf_kind = m.brdf_kind; mats[i].brdf_pigment = m.brdf_pigment; mats[i].emitted_pigment = m.emitted_pigment;
-    mats[i].uses_uv = (d->pigments[m.brdf_pigment].kind != RT_PIGMENT_UNIFORM) ||
-                      (d->pigments[m.emitted_pigment].kind != RT_PIGMENT_UNIFORM);
+    const rt_pigment& pb = d->pigments[m.brdf_pigment];
+    const rt_pigment& pe = d->pigments[m.emitted_pigment];
+    int flags = 0;
+    if (pb.kind != RT_PIGMENT_UNIFORM) flags |= MAT_UV_BRDF;
+    if (pe.kind != RT_PIGMENT_UNIFORM) flags |= MAT_UV_EMIT;
+    // (the float casts are what the fp32 kernels see; a colour that only rounds to zero in fp32 is
+    // not "black" for the fp64 kernels, which do not read these two flags)
+    if (pe.kind == RT_PIGMENT_UNIFORM && pe.color1[0] == 0.0 && pe.color1[1] == 0.0 && pe.color1[2] == 0.0) flags |= MAT_EMIT_BLACK;
+    if (pb.kind == RT_PIGMENT_UNIFORM && !(std::max(std::max(pb.color1[0], pb.color1[1]), pb.color1[2]) > 0.0)) flags |= MAT_NO_SCATTER;
+    mats[i].flags = flags;
     mats[i].threshold = m.threshold_angle_rad;
   }
   UP(materials, mats)
@@ -355,7 +365,8 @@ extern "C" int rt_render_device(rt_scene* s, const rt_render_params* p, void* d_
   int variant = p->variant;
   if (pt) {
     if (p->num_of_rays < 1 || p->max_depth < 0) return fail(RT_ERR_INVALID, "num_of_rays %d, max_depth %d", p->num_of_rays, p->max_depth);
-    if (variant == RT_VARIANT_AUTO) variant = (p->rng_mode == RT_RNG_REPLAY || precision == RT_PRECISION_F64) ? RT_VARIANT_MEGA : RT_VARIANT_WARP;
+    if (variant == RT_VARIANT_AUTO)
+      variant = (p->rng_mode == RT_RNG_REPLAY || precision == RT_PRECISION_F64 || p->max_depth < 0) ? RT_VARIANT_MEGA : RT_VARIANT_WARP;
     if (variant == RT_VARIANT_WARP && (p->rng_mode == RT_RNG_REPLAY || precision == RT_PRECISION_F64))
       return fail(RT_ERR_INVALID, "the warp variant is fp32 with per-sample streams; replay / fp64 need the mega variant");
     if (p->rng_mode == RT_RNG_REPLAY) {

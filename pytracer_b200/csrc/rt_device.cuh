@@ -23,8 +23,15 @@ struct DevPigment {
 };
 struct DevMaterial {
   int32_t brdf_kind, brdf_pigment, emitted_pigment;
-  int32_t uses_uv;  // 0 when both pigments are uniform: the hit record can skip atan2 / acos
+  int32_t flags;  // MAT_*: what shading this material can skip (set once by rt_scene_create)
   double threshold;
+};
+enum {
+  MAT_UV_BRDF = 1,     // the BRDF pigment is not uniform: shading needs (u, v)
+  MAT_UV_EMIT = 2,     // the emitted-radiance pigment is not uniform
+  MAT_EMIT_BLACK = 4,  // emitted radiance is uniform black: the emitted term is zero
+  MAT_NO_SCATTER = 8,  // the BRDF pigment is uniform with no positive channel: render.py:125 never scatters
+  MAT_USES_UV = MAT_UV_BRDF | MAT_UV_EMIT
 };
 struct DevLight {
   double pos[3], color[3], radius;
@@ -46,6 +53,7 @@ template <typename T> struct SceneView {
   // fp32 only: [n_pairs][24] element-interleaved sphere pairs followed by [n_planes][12] planes
   const float* packed;
   int32_t n_pairs, _pad;
+  int32_t n_materials, n_pigments;
 };
 
 template <typename T> struct Hit {
@@ -466,6 +474,17 @@ RT_DEV void closest_all_warp(const SceneView<float>& sc, const ScanSrc<float>& s
   }
 }
 
+// Scenes of a handful of shapes (demo.txt: one sphere, two planes): no sweep / candidate list, every
+// sphere is tested directly from the plain [n][12] table (held in shared memory by the caller).
+RT_DEV void closest_few(const SceneView<float>& sc, const Ray<float>& r, float& best_t, int& best, int origin) {
+#pragma unroll 1
+  for (int i = 0; i < sc.n_spheres; ++i) {
+    const float t = sphere_t_at(sc.invm + 12 * i, r, i == origin);
+    if (t < best_t) { best_t = t; best = i; }
+  }
+  scan_plane_block(sc.invm + 12 * sc.n_spheres, sc.n_spheres, sc.n_shapes - sc.n_spheres, sc.orig, r, best_t, best, origin);
+}
+
 template <bool UNROLL2>
 RT_DEV void closest_all_f32(const SceneView<float>& sc, const ScanSrc<float>& src, const Ray<float>& r,
                             float& best_t, int& best, int origin = -1) {
@@ -498,33 +517,39 @@ template <> RT_DEV bool any_all<float>(const SceneView<float>& sc, const ScanSrc
   return any_candidate_blocks(sc.invm, sc.n_spheres, cand, nc, r);
 }
 
-// Hit record of the winning shape (shapes.py:123-131 / :176-189) + world.py:66-67
-template <typename T>
-RT_DEV void finish_hit(const SceneView<T>& sc, const Ray<T>& r, T t, int idx, Hit<T>& h, bool normalise = true,
-                       bool force_uv = false) {
-  const T* im = sc.invm + 12 * (size_t)idx;
-  const T* mm = sc.m + 12 * (size_t)idx;
+// Hit record of the winning shape (shapes.py:123-131 / :176-189) + world.py:66-67, in three steps so
+// that a caller can stop after the one it needs (the path tracer needs nothing but the emitted colour
+// for a ray whose children would be cut, and no world frame when the surface does not scatter):
+//   local_hit    ray and hit point in the shape's frame
+//   local_uv     surface coordinates (shapes.py:36-42 sphere, :186-187 plane)
+//   world_frame  world point and normal (shapes.py:45-54 / :176-183, normalised like world.py:66-67)
+template <typename T> struct LocalHit {
+  V3<T> hp, d;
+};
+template <typename T> RT_DEV LocalHit<T> local_hit(const T* im, const Ray<T>& r, T t) {
+  LocalHit<T> L;
   V3<T> o = xf_point(im, r.o);
-  V3<T> d = xf_vec(im, r.d);
-  V3<T> hp = o + t * d;
-  h.idx = idx;
-  h.t = t;
-  h.point = xf_point(mm, hp);
-  V3<T> n;
-  h.u = h.v = (T)0;
-  if (idx < sc.n_spheres) {
-    n = (dot(hp, d) < (T)0) ? hp : -hp;  // shapes.py:45-54
-    if (force_uv || sc.materials[sc.material[idx]].uses_uv) {
-      T u = Num<T>::atan2(hp.y, hp.x) / (T)(2.0 * 3.14159265358979323846);  // shapes.py:36-42
-      h.u = (u >= (T)0) ? u : u + (T)1;
-      T z = Num<T>::min((T)1, Num<T>::max((T)-1, hp.z));  // the reference would raise outside [-1,1]
-      h.v = Num<T>::acos(z) / (T)3.14159265358979323846;
-    }
+  L.d = xf_vec(im, r.d);
+  L.hp = o + t * L.d;
+  return L;
+}
+template <typename T> RT_DEV void local_uv(const LocalHit<T>& L, bool sphere, T& u_out, T& v_out) {
+  if (sphere) {
+    T u = Num<T>::atan2(L.hp.y, L.hp.x) / (T)(2.0 * 3.14159265358979323846);  // shapes.py:36-42
+    u_out = (u >= (T)0) ? u : u + (T)1;
+    T z = Num<T>::min((T)1, Num<T>::max((T)-1, L.hp.z));  // the reference would raise outside [-1,1]
+    v_out = Num<T>::acos(z) / (T)3.14159265358979323846;
   } else {
-    n = mk3<T>((T)0, (T)0, (d.z < (T)0) ? (T)1 : (T)-1);
-    h.u = hp.x - Num<T>::floor(hp.x);
-    h.v = hp.y - Num<T>::floor(hp.y);
+    u_out = L.hp.x - Num<T>::floor(L.hp.x);
+    v_out = L.hp.y - Num<T>::floor(L.hp.y);
   }
+}
+template <typename T>
+RT_DEV void world_frame(const T* im, const T* mm, const LocalHit<T>& L, bool sphere, bool normalise, V3<T>& point, V3<T>& normal) {
+  point = xf_point(mm, L.hp);
+  V3<T> n;
+  if (sphere) n = (dot(L.hp, L.d) < (T)0) ? L.hp : -L.hp;  // shapes.py:45-54
+  else n = mk3<T>((T)0, (T)0, (L.d.z < (T)0) ? (T)1 : (T)-1);
   n = xf_normal(im, n);
   if (normalise) {
     if (Num<T>::is_f64) {  // Normal.normalize geometry.py:220-226
@@ -534,7 +559,21 @@ RT_DEV void finish_hit(const SceneView<T>& sc, const Ray<T>& r, T t, int idx, Hi
       n = normalize(n);
     }
   }
-  h.normal = n;
+  normal = n;
+}
+
+template <typename T>
+RT_DEV void finish_hit(const SceneView<T>& sc, const Ray<T>& r, T t, int idx, Hit<T>& h, bool normalise = true,
+                       bool force_uv = false) {
+  const T* im = sc.invm + 12 * (size_t)idx;
+  const bool sphere = idx < sc.n_spheres;
+  const LocalHit<T> L = local_hit<T>(im, r, t);
+  h.idx = idx;
+  h.t = t;
+  h.u = h.v = (T)0;
+  // a plane's (u, v) cost two floors; a sphere's atan2 / acos are skipped when no pigment reads them
+  if (!sphere || force_uv || (sc.materials[sc.material[idx]].flags & MAT_USES_UV)) local_uv<T>(L, sphere, h.u, h.v);
+  world_frame<T>(im, sc.m + 12 * (size_t)idx, L, sphere, normalise, h.point, h.normal);
 }
 
 // ---------------------------------------------------------------- pigments

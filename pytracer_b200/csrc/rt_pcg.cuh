@@ -45,9 +45,13 @@ struct JumpTable {
 };
 
 RT_DEV uint64_t pcg_jump(uint64_t state, uint64_t delta, const JumpTable& t) {
+  delta &= (1ull << RT_JUMP_BITS) - 1ull;
 #pragma unroll 1
-  for (int b = 0; delta != 0 && b < RT_JUMP_BITS; ++b, delta >>= 1)
-    if (delta & 1) state = state * t.mult[b] + t.plus[b];
+  while (delta != 0) {  // one multiply-add per SET bit
+    const int b = __ffsll((long long)delta) - 1;
+    state = state * t.mult[b] + t.plus[b];
+    delta &= delta - 1;
+  }
   return state;
 }
 

@@ -40,6 +40,36 @@ struct WarpCfg {
   long long n_tasks;
 };
 
+// SMALL instantiation: every table of the scene lives in shared memory (a few KB), laid out by
+// this one function on both sides of the launch.
+struct SmallLayout {
+  int invm, m, orig, material, materials, pigments, bytes;
+};
+__host__ __device__ inline SmallLayout small_layout(int n_shapes, int n_materials, int n_pigments) {
+  SmallLayout l;
+  int o = 0;
+  l.invm = o; o += n_shapes * 48;
+  l.m = o; o += n_shapes * 48;
+  l.orig = o; o += n_shapes * 4;
+  l.material = o; o += n_shapes * 4;
+  o = (o + 15) & ~15;
+  l.materials = o; o += n_materials * (int)sizeof(DevMaterial);
+  o = (o + 15) & ~15;
+  l.pigments = o; o += n_pigments * (int)sizeof(DevPigment);
+  l.bytes = (o + 15) & ~15;
+  return l;
+}
+#define RT_SMALL_MAX_SPHERES 8
+#define RT_SMALL_MAX_SHAPES 16
+#define RT_SMALL_MAX_MATERIALS 16
+#define RT_SMALL_MAX_PIGMENTS 32
+
+RT_DEV void stage_words(void* sh, const void* g, int bytes) {  // 4-byte granularity
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(sh);
+  for (int i = threadIdx.x; i < bytes / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
 RT_DEV int own_stratum(const RenderArgs& a, int ls) {
   return (a.part_mode == RT_PART_SPP && a.part_count > 1) ? a.part_rank + ls * a.part_count : ls;
 }
@@ -64,7 +94,23 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   ScanSrc<float> src = global_src<float>(sc);
-  if (SHAPES_SMEM) {
+  SceneView<float> ss = sc;  // the view the per-ray code reads: shared-memory copies for SMALL
+  if (SMALL) {
+    const SmallLayout sl = small_layout(sc.n_shapes, sc.n_materials, sc.n_pigments);
+    stage_words(smem_raw + sl.invm, sc.invm, sc.n_shapes * 48);
+    stage_words(smem_raw + sl.m, sc.m, sc.n_shapes * 48);
+    stage_words(smem_raw + sl.orig, sc.orig, sc.n_shapes * 4);
+    stage_words(smem_raw + sl.material, sc.material, sc.n_shapes * 4);
+    stage_words(smem_raw + sl.materials, sc.materials, sc.n_materials * (int)sizeof(DevMaterial));
+    stage_words(smem_raw + sl.pigments, sc.pigments, sc.n_pigments * (int)sizeof(DevPigment));
+    __syncthreads();
+    ss.invm = reinterpret_cast<const float*>(smem_raw + sl.invm);
+    ss.m = reinterpret_cast<const float*>(smem_raw + sl.m);
+    ss.orig = reinterpret_cast<const int32_t*>(smem_raw + sl.orig);
+    ss.material = reinterpret_cast<const int32_t*>(smem_raw + sl.material);
+    ss.materials = reinterpret_cast<const DevMaterial*>(smem_raw + sl.materials);
+    ss.pigments = reinterpret_cast<const DevPigment*>(smem_raw + sl.pigments);
+  } else if (SHAPES_SMEM) {
     stage_bytes(smem_raw, sc.packed, (size_t)sc.n_pairs * 96 + (size_t)(sc.n_shapes - sc.n_spheres) * 48);
     __syncthreads();
     src.pairs = reinterpret_cast<const float4*>(smem_raw);
@@ -97,6 +143,13 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
     task = __shfl_sync(FULL, task, 0);
     if (task >= cfg.n_tasks) break;
     const long long p0 = task * G;
+    // one pixel per task: the jitter stream is taken to the pixel's first draw once, lanes jump on by 2 s
+    uint64_t aa_task = a.aa_state;
+    if (ACC == ACC_REG && a.S > 0 && p0 < pm.n_pixels) {
+      int col, row;
+      pm.locate(p0, col, row);
+      aa_task = pcg_jump(a.aa_state, 2ull * (unsigned long long)((long long)row * a.width + col) * S2, a.jump);
+    }
     float sr = 0.f, sg = 0.f, sb = 0.f;  // lane-private sums (single-slot tasks)
     unsigned int task_rays = 0;
     if (MULTI_SLOT) {
@@ -136,7 +189,8 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
             const unsigned long long k = (unsigned long long)pix * S2 + s;
             Pcg aa;
             aa.inc = a.aa_inc;
-            aa.state = (a.S > 0) ? pcg_jump(a.aa_state, 2ull * k, a.jump) : 0;
+            if (ACC == ACC_REG) aa.state = (a.S > 0) ? pcg_jump(aa_task, 2ull * (unsigned)s, a.jump) : 0;
+            else aa.state = (a.S > 0) ? pcg_jump(a.aa_state, 2ull * k, a.jump) : 0;
             ray = primary_ray<float>(a, col, row, s, aa);
             rng = pcg_seed(a.pt_state, (a.pt_inc >> 1) + k);
             last_of_pixel = (ls == L - 1);
@@ -213,41 +267,62 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
           closest_all_warp(sc, src, ray, active, best_t, best, origin);
         }
         if (active) {
-          Hit<float> h;
-          if (SMALL) closest_all_f32<false>(sc, src, ray, best_t, best, origin);
+          if (SMALL) closest_few(ss, ray, best_t, best, origin);
           else if (!RT_WARP_SPLIT) closest_all_f32<true>(sc, src, ray, best_t, best, origin);
           const bool found = best >= 0;
-          if (found) finish_hit<float>(sc, ray, best_t, best, h);
           ++n_rays;
           if (count_rays) {
             if (MULTI_SLOT) atomicAdd(&slot_rays[slot], 1);
             else ++task_rays;
           } else if (primary_phase && last_of_pixel && a.out_hit) {
-            a.out_hit[pix] = found ? sc.orig[h.idx] : -1;
+            a.out_hit[pix] = found ? ss.orig[best] : -1;
           }
           if (!found) {
             contrib = mul3(thr, background);
           } else {
-            const DevMaterial& mat = sc.materials[sc.material[h.idx]];
-            V3<float> hit_color = pigment_color<float>(sc.pigments, mat.brdf_pigment, h.u, h.v);
-            const V3<float> emitted = pigment_color<float>(sc.pigments, mat.emitted_pigment, h.u, h.v);
-            contrib = mul3(thr, emitted);
-            const float lum = max3(hit_color);
-            bool go_on = true;
-            if (depth >= a.rr_limit) {  // render.py:116-123
-              const float q = fmaxf(0.05f, 1.f - lum);
-              if (pcg_random_float<float>(rng) > q) hit_color = (1.f / (1.f - q)) * hit_color;
-              else go_on = false;
-            }
-            if (go_on && lum > 0.f && depth < a.max_depth) {
-              push = true;
-              const V3<float> nd = (mat.brdf_kind == RT_BRDF_DIFFUSE) ? h.normal : specular_dir<float>(ray.d, h.normal);
-              const V3<float> w = inv_n * mul3(thr, hit_color);
-              out.a = make_float4(h.point.x, h.point.y, h.point.z,
-                                  __int_as_float(slot | (mat.brdf_kind << 5) | ((depth + 1) << 6) |
-                                                 ((h.idx < 0xFFFF ? h.idx : 0xFFFF) << 16)));
-              out.b = make_float4(nd.x, nd.y, nd.z, w.x);
-              out.c = make_float4(w.y, w.z, __uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)));
+            // The hit record is built lazily (rt_device.cuh local_hit / local_uv / world_frame): most rays
+            // of a tree are its leaves, whose children render.py:100-101 cuts — for those only the emitted
+            // colour matters, which for a uniform pigment needs no record at all.
+            const DevMaterial& mat = ss.materials[ss.material[best]];
+            const int mf = mat.flags;
+            const bool sphere = best < ss.n_spheres;
+            const float* im = ss.invm + 12 * best;
+            float u = 0.f, v = 0.f;
+            if (depth >= a.max_depth) {
+              // every child would come back BLACK, so neither the roulette draw (render.py:116-123) nor
+              // the BRDF colour can change the result: emitted radiance only
+              if (!(mf & MAT_EMIT_BLACK)) {
+                if (mf & MAT_UV_EMIT) local_uv<float>(local_hit<float>(im, ray, best_t), sphere, u, v);
+                contrib = mul3(thr, pigment_color<float>(ss.pigments, mat.emitted_pigment, u, v));
+              }
+            } else {
+              const bool scatters = !(mf & MAT_NO_SCATTER);
+              LocalHit<float> lh;
+              if (scatters || (mf & MAT_USES_UV)) lh = local_hit<float>(im, ray, best_t);
+              if (mf & MAT_USES_UV) local_uv<float>(lh, sphere, u, v);
+              if (!(mf & MAT_EMIT_BLACK)) contrib = mul3(thr, pigment_color<float>(ss.pigments, mat.emitted_pigment, u, v));
+              if (scatters) {
+                V3<float> hit_color = pigment_color<float>(ss.pigments, mat.brdf_pigment, u, v);
+                const float lum = max3(hit_color);
+                bool go_on = true;
+                if (depth >= a.rr_limit) {  // render.py:116-123
+                  const float q = fmaxf(0.05f, 1.f - lum);
+                  if (pcg_random_float<float>(rng) > q) hit_color = fast_rcp(1.f - q) * hit_color;
+                  else go_on = false;
+                }
+                if (go_on && lum > 0.f) {
+                  push = true;
+                  V3<float> point, normal;
+                  world_frame<float>(im, ss.m + 12 * best, lh, sphere, true, point, normal);
+                  const V3<float> nd = (mat.brdf_kind == RT_BRDF_DIFFUSE) ? normal : specular_dir<float>(ray.d, normal);
+                  const V3<float> w = inv_n * mul3(thr, hit_color);
+                  out.a = make_float4(point.x, point.y, point.z,
+                                      __int_as_float(slot | (mat.brdf_kind << 5) | ((depth + 1) << 6) |
+                                                     ((best < 0xFFFF ? best : 0xFFFF) << 16)));
+                  out.b = make_float4(nd.x, nd.y, nd.z, w.x);
+                  out.c = make_float4(w.y, w.z, __uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)));
+                }
+              }
             }
           }
         }
@@ -353,6 +428,7 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
     L = a.part_rank < S2 ? (S2 - a.part_rank + a.part_count - 1) / a.part_count : 0;
   if (pm.n_pixels == 0 || L == 0) return cudaSuccess;
   if (a.num_of_rays < 1) { *why_not = "num_of_rays must be >= 1"; return cudaErrorInvalidValue; }
+  if (a.max_depth < 0) { *why_not = "max_depth < 0 (an all-black image) is left to the mega variant"; return cudaErrorInvalidValue; }
   if (a.max_depth >= 1023) { *why_not = "max_depth >= 1023 is not supported by the warp variant (use mega)"; return cudaErrorInvalidValue; }
   WarpCfg cfg;
   cfg.per_pixel = L;
@@ -361,7 +437,8 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   // warp-full per task so that two CTAs still fit an SM.
   size_t shape_bytes = (size_t)sc.n_pairs * 96 + (size_t)(sc.n_shapes - sc.n_spheres) * 48;
   const bool shapes_smem = shape_bytes > 0 && shape_bytes <= 64 * 1024;
-  const bool small = sc.n_spheres <= 8 && shapes_smem;
+  const bool small = sc.n_shapes > 0 && sc.n_spheres <= RT_SMALL_MAX_SPHERES && sc.n_shapes <= RT_SMALL_MAX_SHAPES &&
+                     sc.n_materials <= RT_SMALL_MAX_MATERIALS && sc.n_pigments <= RT_SMALL_MAX_PIGMENTS;
   const int want = small ? 64 : 32;
   if (L >= 32) cfg.group = 1;
   else if (L >= 4) cfg.group = (want + L - 1) / L < RT_ACC_LANES_MAX_GROUP ? (want + L - 1) / L : RT_ACC_LANES_MAX_GROUP;
@@ -376,7 +453,8 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   long long cap = a.num_of_rays == 1 ? prims + 32 : prims + 32ll * (long long)a.max_depth;
   if (cap < 64) cap = 64;
   const int acc_mode = cfg.group == 1 ? ACC_REG : (cfg.group <= RT_ACC_LANES_MAX_GROUP ? ACC_LANES : ACC_SEG);
-  cfg.shape_bytes = shapes_smem ? (int)((shape_bytes + 15) / 16 * 16) : 0;
+  cfg.shape_bytes = small ? small_layout(sc.n_shapes, sc.n_materials, sc.n_pigments).bytes
+                          : (shapes_smem ? (int)((shape_bytes + 15) / 16 * 16) : 0);
   const size_t limit = 200 * 1024;
   int warps = RT_WARP_MAX_THREADS / 32;
   size_t per_warp = 0, smem = 0;
