@@ -14,7 +14,8 @@ from pathlib import Path
 from . import _abi
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libpytracer_b200.so"
+# PYTRACER_B200_LIB: another build of the same library (kernel tuning experiments)
+LIB_PATH = Path(os.environ.get("PYTRACER_B200_LIB") or _PKG / "libpytracer_b200.so")
 _lock = threading.Lock()
 _lib = None
 

@@ -3,13 +3,14 @@
 # multiply-add fusion so that they round like the reference's Python arithmetic.
 set -euo pipefail
 cd "$(dirname "$0")"
-OUT=../libpytracer_b200.so
+OUT=${RT_OUT:-../libpytracer_b200.so}
+B=${RT_BUILD_DIR:-build}
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 COMMON="${RT_EXTRA_FLAGS:-} -O3 -std=c++17 -lineinfo -Xcompiler -fPIC"
-mkdir -p build
-nvcc $ARCH $COMMON -c rt_kernels_f32.cu -o build/rt_kernels_f32.o &
-nvcc $ARCH $COMMON --fmad=false -c rt_kernels_f64.cu -o build/rt_kernels_f64.o &
-nvcc $ARCH $COMMON -c rt_api.cu -o build/rt_api.o &
+mkdir -p $B
+nvcc $ARCH $COMMON -c rt_kernels_f32.cu -o $B/rt_kernels_f32.o &
+nvcc $ARCH $COMMON --fmad=false -c rt_kernels_f64.cu -o $B/rt_kernels_f64.o &
+nvcc $ARCH $COMMON -c rt_api.cu -o $B/rt_api.o &
 wait
-nvcc $ARCH -shared -o $OUT build/rt_kernels_f32.o build/rt_kernels_f64.o build/rt_api.o -lcudart_static -lpthread -ldl -lrt
+nvcc $ARCH -shared -o $OUT $B/rt_kernels_f32.o $B/rt_kernels_f64.o $B/rt_api.o -lcudart_static -lpthread -ldl -lrt
 [ -f $OUT ] && echo "built $(realpath $OUT)"

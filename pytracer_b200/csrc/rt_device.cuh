@@ -475,14 +475,41 @@ RT_DEV void closest_all_warp(const SceneView<float>& sc, const ScanSrc<float>& s
 }
 
 // Scenes of a handful of shapes (demo.txt: one sphere, two planes): no sweep / candidate list, every
-// sphere is tested directly from the plain [n][12] table (held in shared memory by the caller).
+// shape is tested directly from the plain [n][12] table (held in shared memory by the caller), and the
+// tests are written without branches: with 32 different rays per warp some lane crosses every shape
+// anyway, so a branch only adds its own overhead.  Same decisions as sphere_t_at / plane_t.
+RT_DEV float sphere_t_few(const float* __restrict__ im, const Ray<float>& r, bool is_origin) {
+  float a, hb;
+  const float qd = sphere_qdelta(im, r, a, hb);
+  const float sd = fast_sqrt(fmaxf(qd, 0.0f)), inv = fast_rcp(a);
+  const float t1 = (-hb - sd) * inv, t2 = (-hb + sd) * inv;
+  float t = (t1 > r.tmin && t1 < r.tmax) ? t1 : t2;  // the first root inside (tmin, tmax), shapes.py:112-119
+  bool ok = qd > 0.0f;
+  if (is_origin) { t = -2.0f * hb * inv; ok = true; }  // see sphere_t_at
+  return (ok && t > r.tmin && t < r.tmax) ? t : Num<float>::inf();
+}
+RT_DEV float plane_t_few(const float* __restrict__ im, const Ray<float>& r, bool is_origin) {
+  const float4 row = reinterpret_cast<const float4*>(im)[2];
+  const float oz = fmaf(r.o.x, row.x, fmaf(r.o.y, row.y, fmaf(r.o.z, row.z, row.w)));
+  const float dz = fmaf(r.d.x, row.x, fmaf(r.d.y, row.y, r.d.z * row.z));
+  const float t = -oz * fast_rcp(dz);
+  const bool ok = !(fabsf(dz) < 1e-5f) && t > r.tmin && t < r.tmax && !is_origin;
+  return ok ? t : Num<float>::inf();
+}
 RT_DEV void closest_few(const SceneView<float>& sc, const Ray<float>& r, float& best_t, int& best, int origin) {
 #pragma unroll 1
   for (int i = 0; i < sc.n_spheres; ++i) {
-    const float t = sphere_t_at(sc.invm + 12 * i, r, i == origin);
+    const float t = sphere_t_few(sc.invm + 12 * i, r, i == origin);
     if (t < best_t) { best_t = t; best = i; }
   }
-  scan_plane_block(sc.invm + 12 * sc.n_spheres, sc.n_spheres, sc.n_shapes - sc.n_spheres, sc.orig, r, best_t, best, origin);
+#pragma unroll 1
+  for (int i = sc.n_spheres; i < sc.n_shapes; ++i) {
+    const float t = plane_t_few(sc.invm + 12 * i, r, i == origin);
+    if (t < best_t) { best_t = t; best = i; }
+    else if (t == best_t && best >= 0 && best < sc.n_spheres) {  // world.py:62 on a sphere / plane tie
+      if (plane_wins_tie(sc.orig, i, best)) { best_t = t; best = i; }
+    }
+  }
 }
 
 template <bool UNROLL2>

@@ -38,31 +38,34 @@ struct WarpCfg {
   int per_warp_bytes;
   int shape_bytes;    // shared memory reserved for the shape block (0 = read from global)
   long long n_tasks;
+  // values every iteration needs, precomputed so that they are constant-bank operands instead of
+  // registers: background colour in fp32, 1/N, 1/spp, the multiply-shift magic for x / N
+  float bg[3], inv_n, inv_spp;
+  unsigned n_magic;
+  unsigned long long n_samples;  // samples this launch traces (all tasks), added to the counter once
 };
 
-// SMALL instantiation: every table of the scene lives in shared memory (a few KB), laid out by
-// this one function on both sides of the launch.
-struct SmallLayout {
-  int invm, m, orig, material, materials, pigments, bytes;
-};
-__host__ __device__ inline SmallLayout small_layout(int n_shapes, int n_materials, int n_pigments) {
-  SmallLayout l;
-  int o = 0;
-  l.invm = o; o += n_shapes * 48;
-  l.m = o; o += n_shapes * 48;
-  l.orig = o; o += n_shapes * 4;
-  l.material = o; o += n_shapes * 4;
-  o = (o + 15) & ~15;
-  l.materials = o; o += n_materials * (int)sizeof(DevMaterial);
-  o = (o + 15) & ~15;
-  l.pigments = o; o += n_pigments * (int)sizeof(DevPigment);
-  l.bytes = (o + 15) & ~15;
-  return l;
-}
+// SMALL instantiation: every table of the scene lives in shared memory at FIXED offsets (capacity
+// for the largest small scene, 5.6 KB), so that table addresses are immediates in the per-ray code.
 #define RT_SMALL_MAX_SPHERES 8
 #define RT_SMALL_MAX_SHAPES 16
 #define RT_SMALL_MAX_MATERIALS 16
 #define RT_SMALL_MAX_PIGMENTS 32
+enum {
+  SM_INVM = 0,
+  SM_M = SM_INVM + RT_SMALL_MAX_SHAPES * 48,
+  SM_ORIG = SM_M + RT_SMALL_MAX_SHAPES * 48,
+  SM_MATERIAL = SM_ORIG + RT_SMALL_MAX_SHAPES * 4,
+  SM_MATERIALS = SM_MATERIAL + RT_SMALL_MAX_SHAPES * 4,
+  SM_PIGMENTS = (SM_MATERIALS + RT_SMALL_MAX_MATERIALS * (int)sizeof(DevMaterial) + 15) / 16 * 16,
+  SM_BYTES = (SM_PIGMENTS + RT_SMALL_MAX_PIGMENTS * (int)sizeof(DevPigment) + 15) / 16 * 16
+};
+#ifndef RT_SMALL_THREADS
+#define RT_SMALL_THREADS 256
+#endif
+#ifndef RT_SMALL_MINB
+#define RT_SMALL_MINB 3
+#endif
 
 RT_DEV void stage_words(void* sh, const void* g, int bytes) {  // 4-byte granularity
   const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
@@ -87,7 +90,7 @@ enum { ACC_REG = 0, ACC_LANES = 1, ACC_SEG = 2 };
 #define RT_ACC_LANES_MAX_GROUP 8
 
 template <bool SHAPES_SMEM, int ACC, bool SMALL>
-__global__ void __launch_bounds__(RT_WARP_MAX_THREADS, SMALL ? 3 : 2)
+__global__ void __launch_bounds__(SMALL ? RT_SMALL_THREADS : RT_WARP_MAX_THREADS, SMALL ? RT_SMALL_MINB : 2)
 k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ RenderArgs a,
           const __grid_constant__ WarpCfg cfg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -96,27 +99,26 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
   ScanSrc<float> src = global_src<float>(sc);
   SceneView<float> ss = sc;  // the view the per-ray code reads: shared-memory copies for SMALL
   if (SMALL) {
-    const SmallLayout sl = small_layout(sc.n_shapes, sc.n_materials, sc.n_pigments);
-    stage_words(smem_raw + sl.invm, sc.invm, sc.n_shapes * 48);
-    stage_words(smem_raw + sl.m, sc.m, sc.n_shapes * 48);
-    stage_words(smem_raw + sl.orig, sc.orig, sc.n_shapes * 4);
-    stage_words(smem_raw + sl.material, sc.material, sc.n_shapes * 4);
-    stage_words(smem_raw + sl.materials, sc.materials, sc.n_materials * (int)sizeof(DevMaterial));
-    stage_words(smem_raw + sl.pigments, sc.pigments, sc.n_pigments * (int)sizeof(DevPigment));
+    stage_words(smem_raw + SM_INVM, sc.invm, sc.n_shapes * 48);
+    stage_words(smem_raw + SM_M, sc.m, sc.n_shapes * 48);
+    stage_words(smem_raw + SM_ORIG, sc.orig, sc.n_shapes * 4);
+    stage_words(smem_raw + SM_MATERIAL, sc.material, sc.n_shapes * 4);
+    stage_words(smem_raw + SM_MATERIALS, sc.materials, sc.n_materials * (int)sizeof(DevMaterial));
+    stage_words(smem_raw + SM_PIGMENTS, sc.pigments, sc.n_pigments * (int)sizeof(DevPigment));
     __syncthreads();
-    ss.invm = reinterpret_cast<const float*>(smem_raw + sl.invm);
-    ss.m = reinterpret_cast<const float*>(smem_raw + sl.m);
-    ss.orig = reinterpret_cast<const int32_t*>(smem_raw + sl.orig);
-    ss.material = reinterpret_cast<const int32_t*>(smem_raw + sl.material);
-    ss.materials = reinterpret_cast<const DevMaterial*>(smem_raw + sl.materials);
-    ss.pigments = reinterpret_cast<const DevPigment*>(smem_raw + sl.pigments);
+    ss.invm = reinterpret_cast<const float*>(smem_raw + SM_INVM);
+    ss.m = reinterpret_cast<const float*>(smem_raw + SM_M);
+    ss.orig = reinterpret_cast<const int32_t*>(smem_raw + SM_ORIG);
+    ss.material = reinterpret_cast<const int32_t*>(smem_raw + SM_MATERIAL);
+    ss.materials = reinterpret_cast<const DevMaterial*>(smem_raw + SM_MATERIALS);
+    ss.pigments = reinterpret_cast<const DevPigment*>(smem_raw + SM_PIGMENTS);
   } else if (SHAPES_SMEM) {
     stage_bytes(smem_raw, sc.packed, (size_t)sc.n_pairs * 96 + (size_t)(sc.n_shapes - sc.n_spheres) * 48);
     __syncthreads();
     src.pairs = reinterpret_cast<const float4*>(smem_raw);
     src.planes = reinterpret_cast<const float*>(smem_raw) + 24 * (size_t)sc.n_pairs;
   }
-  unsigned char* wbase = smem_raw + cfg.shape_bytes + (size_t)warp * cfg.per_warp_bytes;
+  unsigned char* wbase = smem_raw + (SMALL ? (int)SM_BYTES : cfg.shape_bytes) + warp * cfg.per_warp_bytes;
   ScatterRec* stack = reinterpret_cast<ScatterRec*>(wbase);
   ScatterRec* cur = stack + cfg.cap;
   constexpr bool MULTI_SLOT = ACC != ACC_REG;
@@ -129,12 +131,10 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
   const int S2 = a.S > 0 ? a.S * a.S : 1;
   const int G = cfg.group, L = cfg.per_pixel;
   // x / N for 0 <= x <= 32 as a multiply-shift (exact for N <= 1024; beyond that x / N is 0 or 1)
-  const unsigned n_magic = N <= 1024 ? (65536u + (unsigned)N - 1u) / (unsigned)N : 0u;
-  auto div_n = [&](int x) -> int { return n_magic ? (int)(((unsigned)x * n_magic) >> 16) : (x >= N ? 1 : 0); };
-  const float inv_n = 1.0f / (float)N;
-  const float inv_spp = 1.0f / (float)S2;
-  const V3<float> background = load3<float>(a.background);
-  unsigned int n_rays = 0, n_samples = 0;
+  auto div_n = [&](int x) -> int { return cfg.n_magic ? (int)(((unsigned)x * cfg.n_magic) >> 16) : (x >= N ? 1 : 0); };
+  const float inv_n = cfg.inv_n, inv_spp = cfg.inv_spp;
+  // rays are counted once per iteration from warp-uniform quantities (every lane holds the same sum)
+  unsigned int n_rays = 0;
   bool overflow = false;
 
   while (true) {
@@ -151,7 +151,8 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
       aa_task = pcg_jump(a.aa_state, 2ull * (unsigned long long)((long long)row * a.width + col) * S2, a.jump);
     }
     float sr = 0.f, sg = 0.f, sb = 0.f;  // lane-private sums (single-slot tasks)
-    unsigned int task_rays = 0;
+    unsigned int task_rays = 0;          // warp-uniform
+    const int task_prims = (int)min((long long)G, pm.n_pixels - p0) * L;  // primaries of this task
     if (MULTI_SLOT) {
       if (ACC == ACC_SEG) { for (int i = lane; i < 96; i += 32) acc[i] = 0.f; }
       else { for (int i = 0; i < 3 * cfg.group; ++i) acc[i * 32 + lane] = 0.f; }
@@ -181,6 +182,9 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
           const int ls = j - slot * L;
           const long long p = p0 + slot;
           active = (j < G * L) && (p < pm.n_pixels);
+          const unsigned n_act = (unsigned)min(max(task_prims - round * 32, 0), 32);
+          n_rays += n_act;
+          task_rays += n_act;
           if (active) {
             int col, row;
             pm.locate(p, col, row);
@@ -194,7 +198,6 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
             ray = primary_ray<float>(a, col, row, s, aa);
             rng = pcg_seed(a.pt_state, (a.pt_inc >> 1) + k);
             last_of_pixel = (ls == L - 1);
-            ++n_samples;
           }
           if (ACC == ACC_SEG) seg_start = max(0, slot * L - round * 32);
         } else {
@@ -202,6 +205,8 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
           if (avail == 0) break;
           const int take = (int)min(avail, 32ll);
           active = lane < take;
+          n_rays += (unsigned)take;
+          task_rays += (unsigned)take;
           const int from_cur = min(cur_rem, take);
           ScatterRec rec;
           int child = 0;
@@ -270,15 +275,13 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
           if (SMALL) closest_few(ss, ray, best_t, best, origin);
           else if (!RT_WARP_SPLIT) closest_all_f32<true>(sc, src, ray, best_t, best, origin);
           const bool found = best >= 0;
-          ++n_rays;
           if (count_rays) {
             if (MULTI_SLOT) atomicAdd(&slot_rays[slot], 1);
-            else ++task_rays;
-          } else if (primary_phase && last_of_pixel && a.out_hit) {
-            a.out_hit[pix] = found ? ss.orig[best] : -1;
+          } else if (primary_phase) {  // (warp-uniform)
+            if (last_of_pixel && a.out_hit) a.out_hit[pix] = found ? ss.orig[best] : -1;
           }
           if (!found) {
-            contrib = mul3(thr, background);
+            contrib = mk3<float>(thr.x * cfg.bg[0], thr.y * cfg.bg[1], thr.z * cfg.bg[2]);
           } else {
             // The hit record is built lazily (rt_device.cuh local_hit / local_uv / world_frame): most rays
             // of a tree are its leaves, whose children render.py:100-101 cuts — for those only the emitted
@@ -293,16 +296,20 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
               // the BRDF colour can change the result: emitted radiance only
               if (!(mf & MAT_EMIT_BLACK)) {
                 if (mf & MAT_UV_EMIT) local_uv<float>(local_hit<float>(im, ray, best_t), sphere, u, v);
-                contrib = mul3(thr, pigment_color<float>(ss.pigments, mat.emitted_pigment, u, v));
+                contrib = mul3(thr, (mf & MAT_UV_EMIT) ? pigment_color<float>(ss.pigments, mat.emitted_pigment, u, v)
+                                                       : pig_c1<float>(ss.pigments[mat.emitted_pigment]));
               }
             } else {
               const bool scatters = !(mf & MAT_NO_SCATTER);
               LocalHit<float> lh;
               if (scatters || (mf & MAT_USES_UV)) lh = local_hit<float>(im, ray, best_t);
               if (mf & MAT_USES_UV) local_uv<float>(lh, sphere, u, v);
-              if (!(mf & MAT_EMIT_BLACK)) contrib = mul3(thr, pigment_color<float>(ss.pigments, mat.emitted_pigment, u, v));
+              if (!(mf & MAT_EMIT_BLACK))
+                contrib = mul3(thr, (mf & MAT_UV_EMIT) ? pigment_color<float>(ss.pigments, mat.emitted_pigment, u, v)
+                                                       : pig_c1<float>(ss.pigments[mat.emitted_pigment]));
               if (scatters) {
-                V3<float> hit_color = pigment_color<float>(ss.pigments, mat.brdf_pigment, u, v);
+                V3<float> hit_color = (mf & MAT_UV_BRDF) ? pigment_color<float>(ss.pigments, mat.brdf_pigment, u, v)
+                                                         : pig_c1<float>(ss.pigments[mat.brdf_pigment]);
                 const float lum = max3(hit_color);
                 bool go_on = true;
                 if (depth >= a.rr_limit) {  // render.py:116-123
@@ -405,7 +412,6 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
         sg += __shfl_xor_sync(FULL, sg, d);
         sb += __shfl_xor_sync(FULL, sb, d);
       }
-      task_rays = __reduce_add_sync(FULL, task_rays);
       if (lane == 0 && p0 < pm.n_pixels) {
         int col, row;
         pm.locate(p0, col, row);
@@ -415,8 +421,8 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
     }
   }
   if (overflow) atomicExch(a.counters + CNT_OVERFLOW, 1ull);
-  block_count_add(a.counters + CNT_CLOSEST, n_rays);
-  block_count_add(a.counters + CNT_SAMPLES, n_samples);
+  if (lane == 0 && n_rays) atomicAdd(a.counters + CNT_CLOSEST, (unsigned long long)n_rays);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.counters + CNT_SAMPLES, cfg.n_samples);
 }
 
 inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderArgs& a, cudaStream_t st,
@@ -453,10 +459,9 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   long long cap = a.num_of_rays == 1 ? prims + 32 : prims + 32ll * (long long)a.max_depth;
   if (cap < 64) cap = 64;
   const int acc_mode = cfg.group == 1 ? ACC_REG : (cfg.group <= RT_ACC_LANES_MAX_GROUP ? ACC_LANES : ACC_SEG);
-  cfg.shape_bytes = small ? small_layout(sc.n_shapes, sc.n_materials, sc.n_pigments).bytes
-                          : (shapes_smem ? (int)((shape_bytes + 15) / 16 * 16) : 0);
+  cfg.shape_bytes = small ? (int)SM_BYTES : (shapes_smem ? (int)((shape_bytes + 15) / 16 * 16) : 0);
   const size_t limit = 200 * 1024;
-  int warps = RT_WARP_MAX_THREADS / 32;
+  int warps = (small ? RT_SMALL_THREADS : RT_WARP_MAX_THREADS) / 32;
   size_t per_warp = 0, smem = 0;
   for (;; warps >>= 1) {
     per_warp = (size_t)(cap + 1) * sizeof(ScatterRec);
@@ -468,6 +473,11 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   if (smem > limit) { *why_not = "max_depth needs a deeper work stack than shared memory holds"; return cudaErrorInvalidValue; }
   cfg.cap = (int)cap;
   cfg.per_warp_bytes = (int)per_warp;
+  for (int k = 0; k < 3; ++k) cfg.bg[k] = (float)a.background[k];
+  cfg.inv_n = 1.0f / (float)a.num_of_rays;
+  cfg.inv_spp = 1.0f / (float)S2;
+  cfg.n_magic = a.num_of_rays <= 1024 ? (65536u + (unsigned)a.num_of_rays - 1u) / (unsigned)a.num_of_rays : 0u;
+  cfg.n_samples = (unsigned long long)pm.n_pixels * (unsigned long long)L;
 
   void (*kern)(const SceneView<float>, const RenderArgs, const WarpCfg);
 #define RT_PICK(ACCM)                                                                   \
