@@ -244,6 +244,33 @@ int rt_scatter(rt_scene* scene, int32_t material, int32_t precision, const doubl
 /* create_onb_from_z, geometry.py:247-262: normals double[n][3] -> double[n][9] = e1,e2,e3 */
 int rt_onb(int32_t precision, const double* normals, int32_t n, double* out);
 
+/* ---- tone mapping: the step after the render (main.py:209-215, pfm2png main.py:226-230) ----
+ * rgb: float[n_pixels][3] in HdrImage.pixels order; on_device != 0 means every buffer of the call is
+ * a DEVICE pointer and the kernels run on `stream` (cudaStream_t as void*, NULL = default stream);
+ * otherwise host buffers are copied in and out.  Both calls synchronise the stream before returning.
+ * Arithmetic is fp64 in the reference's operation order on the fp32 pixel values (what the reference
+ * computes on an image read back from a PFM file). */
+typedef struct rt_tonemap_stats {
+  double luminosity;  /* the average luminosity used (computed or passed in) */
+  float lum_ms;       /* CUDA events around the luminosity kernel (0 if luminosity was passed in) */
+  float map_ms;       /* CUDA events around the normalise/clamp/quantise kernel */
+  float total_ms;     /* whole call on the stream, copies included */
+  int32_t n_launches;
+} rt_tonemap_stats;
+/* HdrImage.average_luminosity(delta), hdrimages.py:120-128: 10 ** mean(log10(delta + luminosity)) */
+int rt_average_luminosity(const float* rgb, int64_t n_pixels, double delta, int32_t on_device,
+                          void* stream, double* out);
+/* One pass over the image doing any of: HdrImage.normalize_image(factor, luminosity)
+ * (hdrimages.py:130-140, flag RT_TONE_NORMALIZE), clamp_image() (hdrimages.py:142-147, flag
+ * RT_TONE_CLAMP) -> out_hdr float[n][3] (optional), and write_ldr_image's int(255 * c ** (1 / gamma))
+ * of the result (hdrimages.py:160-165) -> out_ldr uint8[n][3] (optional).  With RT_TONE_NORMALIZE,
+ * luminosity == 0 (or NaN) is the reference's `if not luminosity`: the image's own
+ * average_luminosity() is computed first.  main.py:209-215 = flags 3 with out_ldr. */
+enum { RT_TONE_NORMALIZE = 1, RT_TONE_CLAMP = 2 };
+int rt_tone_map(const float* rgb, int64_t n_pixels, int32_t flags, double factor, double luminosity, double gamma,
+                int32_t on_device, void* stream, float* out_hdr, uint8_t* out_ldr,
+                rt_tonemap_stats* stats);
+
 /* ---- host buffers ----
  * Page-locks / unlocks a caller-owned host buffer (cudaHostRegister) so that rt_render's final
  * device->host copy of the image runs at full PCIe speed.  Optional: pageable buffers work too. */

@@ -126,6 +126,19 @@ class rt_stats(C.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+class rt_tonemap_stats(C.Structure):
+    _fields_ = [
+        ("luminosity", C.c_double),
+        ("lum_ms", C.c_float),
+        ("map_ms", C.c_float),
+        ("total_ms", C.c_float),
+        ("n_launches", C.c_int32),
+    ]
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
 class rt_hit(C.Structure):
     _fields_ = [
         ("shape", C.c_int32),

@@ -40,6 +40,9 @@ _PROTOTYPES = {
     "rt_pigment_color": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
     "rt_scatter": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "rt_onb": (C.c_int, [C.c_int32, _P, C.c_int32, _P]),
+    "rt_average_luminosity": (C.c_int, [_P, C.c_int64, C.c_double, C.c_int32, _P, C.POINTER(C.c_double)]),
+    "rt_tone_map": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32, _P, _P, _P,
+                              C.POINTER(_abi.rt_tonemap_stats)]),
     "rt_host_register": (C.c_int, [_P, C.c_uint64]),
     "rt_host_unregister": (C.c_int, [_P]),
     "rt_bench_ffma": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_float)]),

@@ -11,6 +11,7 @@ mkdir -p $B
 nvcc $ARCH $COMMON -c rt_kernels_f32.cu -o $B/rt_kernels_f32.o &
 nvcc $ARCH $COMMON --fmad=false -c rt_kernels_f64.cu -o $B/rt_kernels_f64.o &
 nvcc $ARCH $COMMON -c rt_api.cu -o $B/rt_api.o &
+nvcc $ARCH $COMMON --fmad=false -c rt_tonemap.cu -o $B/rt_tonemap.o &
 wait
-nvcc $ARCH -shared -o $OUT $B/rt_kernels_f32.o $B/rt_kernels_f64.o $B/rt_api.o -lcudart_static -lpthread -ldl -lrt
+nvcc $ARCH -shared -o $OUT $B/rt_kernels_f32.o $B/rt_kernels_f64.o $B/rt_api.o $B/rt_tonemap.o -lcudart_static -lpthread -ldl -lrt
 [ -f $OUT ] && echo "built $(realpath $OUT)"

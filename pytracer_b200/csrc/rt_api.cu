@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -48,6 +49,15 @@ struct Workspace {
   void* probe_buf = nullptr;
   size_t probe_cap = 0;
   int sm_count = 0;
+  // tone mapping (rt_tonemap.cu): per-block partial sums, completion counter, result; LDR staging
+  double* tm_partials = nullptr;
+  unsigned int* tm_done = nullptr;
+  double* tm_sum = nullptr;
+  double* tm_sum_host = nullptr;  // pinned
+  void* ldr = nullptr;
+  size_t ldr_cap = 0;
+  void* hdr_out = nullptr;
+  size_t hdr_out_cap = 0;
 };
 
 struct rt_scene {
@@ -652,6 +662,112 @@ extern "C" int rt_bench_ffma(int32_t iterations, double* tflops, float* ms_out) 
   double flops = (double)blocks * 256.0 * (double)iterations * 16.0 * 8.0 * 2.0;
   if (tflops) *tflops = flops / (ms * 1e-3) / 1e12;
   if (ms_out) *ms_out = ms;
+  return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------ tone mapping
+static int tonemap_workspace(Workspace** out) {
+  if (rt_device_count() <= 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
+  int device = 0;
+  CU(cudaGetDevice(&device));
+  Workspace* w = nullptr;
+  int rc = get_workspace(device, &w);
+  if (rc != RT_OK) return rc;
+  if (!w->tm_partials) {
+    CU(cudaMalloc((void**)&w->tm_partials, tonemap_max_blocks() * sizeof(double)));
+    CU(cudaMalloc((void**)&w->tm_done, sizeof(unsigned int)));
+    CU(cudaMemset(w->tm_done, 0, sizeof(unsigned int)));
+    CU(cudaMalloc((void**)&w->tm_sum, sizeof(double)));
+    CU(cudaMallocHost((void**)&w->tm_sum_host, sizeof(double)));
+  }
+  *out = w;
+  return RT_OK;
+}
+
+// device image -> average luminosity (hdrimages.py:120-128); synchronises `st`
+static int device_average_luminosity(Workspace* w, const float* d_rgb, int64_t n_pixels, double delta, cudaStream_t st, double* out) {
+  cudaError_t e = launch_lum_sum(d_rgb, n_pixels, delta, w->tm_partials, w->tm_done, w->tm_sum, w->sm_count, st);
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, "luminosity launch: %s", cudaGetErrorString(e));
+  CU(cudaMemcpyAsync(w->tm_sum_host, w->tm_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  *out = pow(10.0, *w->tm_sum_host / (double)n_pixels);
+  return RT_OK;
+}
+
+extern "C" int rt_average_luminosity(const float* rgb, int64_t n_pixels, double delta, int32_t on_device, void* stream, double* out) {
+  if (!rgb || !out) return fail(RT_ERR_INVALID, "rt_average_luminosity: null argument");
+  if (n_pixels <= 0) return fail(RT_ERR_INVALID, "rt_average_luminosity: empty image (the reference divides by len(pixels))");
+  Workspace* w = nullptr;
+  int rc = tonemap_workspace(&w);
+  if (rc != RT_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* d_rgb = rgb;
+  if (!on_device) {
+    const size_t bytes = (size_t)n_pixels * 3 * sizeof(float);
+    if ((rc = ensure(&w->image, &w->image_cap, bytes)) != RT_OK) return rc;
+    CU(cudaMemcpyAsync(w->image, rgb, bytes, cudaMemcpyHostToDevice, st));
+    d_rgb = (const float*)w->image;
+  }
+  return device_average_luminosity(w, d_rgb, n_pixels, delta, st, out);
+}
+
+extern "C" int rt_tone_map(const float* rgb, int64_t n_pixels, int32_t flags, double factor, double luminosity, double gamma,
+                           int32_t on_device, void* stream, float* out_hdr, uint8_t* out_ldr, rt_tonemap_stats* stats) {
+  if (!rgb) return fail(RT_ERR_INVALID, "rt_tone_map: null image");
+  if (n_pixels <= 0) return fail(RT_ERR_INVALID, "rt_tone_map: empty image");
+  if (!(gamma > 0.0)) return fail(RT_ERR_INVALID, "rt_tone_map: gamma %g", gamma);
+  Workspace* w = nullptr;
+  int rc = tonemap_workspace(&w);
+  if (rc != RT_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t px3 = (size_t)n_pixels * 3;
+  const float* d_rgb = rgb;
+  float* d_hdr = out_hdr;
+  unsigned char* d_ldr = out_ldr;
+  CU(cudaEventRecord(w->t0, st));
+  if (!on_device) {
+    if ((rc = ensure(&w->image, &w->image_cap, px3 * sizeof(float))) != RT_OK) return rc;
+    CU(cudaMemcpyAsync(w->image, rgb, px3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    d_rgb = (const float*)w->image;
+    if (out_hdr) { if ((rc = ensure(&w->hdr_out, &w->hdr_out_cap, px3 * sizeof(float))) != RT_OK) return rc; d_hdr = (float*)w->hdr_out; }
+    if (out_ldr) { if ((rc = ensure(&w->ldr, &w->ldr_cap, px3)) != RT_OK) return rc; d_ldr = (unsigned char*)w->ldr; }
+  }
+  int launches = 0;
+  float lum_ms = 0.f, map_ms = 0.f;
+  // hdrimages.py:136-137 `if not luminosity`: None and 0.0 both mean "use the image's own average"
+  if ((flags & RT_TONE_NORMALIZE) && (luminosity == 0.0 || luminosity != luminosity)) {
+    CU(cudaEventRecord(w->ev0, st));
+    cudaError_t e = launch_lum_sum(d_rgb, n_pixels, 1e-10, w->tm_partials, w->tm_done, w->tm_sum, w->sm_count, st);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "luminosity launch: %s", cudaGetErrorString(e));
+    CU(cudaEventRecord(w->ev1, st));
+    CU(cudaMemcpyAsync(w->tm_sum_host, w->tm_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    luminosity = pow(10.0, *w->tm_sum_host / (double)n_pixels);
+    CU(cudaEventElapsedTime(&lum_ms, w->ev0, w->ev1));
+    ++launches;
+  }
+  if (d_hdr || d_ldr) {
+    CU(cudaEventRecord(w->ev0, st));
+    cudaError_t e = launch_tone_map(d_rgb, n_pixels, flags, factor / luminosity, gamma, d_hdr, d_ldr, w->sm_count, st);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "tone map launch: %s", cudaGetErrorString(e));
+    CU(cudaEventRecord(w->ev1, st));
+    ++launches;
+    if (!on_device) {
+      if (out_hdr) CU(cudaMemcpyAsync(out_hdr, d_hdr, px3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+      if (out_ldr) CU(cudaMemcpyAsync(out_ldr, d_ldr, px3, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CU(cudaEventRecord(w->t1, st));
+  CU(cudaStreamSynchronize(st));
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    if (d_hdr || d_ldr) CU(cudaEventElapsedTime(&map_ms, w->ev0, w->ev1));
+    float total = 0.f;
+    CU(cudaEventElapsedTime(&total, w->t0, w->t1));
+    stats->luminosity = luminosity;
+    stats->lum_ms = lum_ms; stats->map_ms = map_ms; stats->total_ms = total;
+    stats->n_launches = launches;
+  }
   return RT_OK;
 }
 

@@ -48,4 +48,11 @@ enum { PROBE_TRACE = 0, PROBE_INTERSECT = 1, PROBE_VISIBLE = 2, PROBE_PIGMENT = 
        PROBE_ONB = 5, PROBE_PCG_DRAW = 6, PROBE_PCG_SEED = 7, PROBE_CAMERA_RAYS = 8, PROBE_CAMERA_UV = 9 };
 template <typename T> cudaError_t launch_probe(const SceneView<T>& sc, const RenderArgs& a, const ProbeArgs& p, cudaStream_t st);
 
+// rt_tonemap.cu: HdrImage.average_luminosity's sum and the normalise / clamp / LDR map (hdrimages.py:120-171)
+int tonemap_max_blocks();
+cudaError_t launch_lum_sum(const float* d_rgb, long long n_pixels, double delta, double* d_partials,
+                           unsigned int* d_done, double* d_out, int sm_count, cudaStream_t st);
+cudaError_t launch_tone_map(const float* d_rgb, long long n_pixels, int flags, double scale, double gamma, float* d_out_hdr,
+                            unsigned char* d_out_ldr, int sm_count, cudaStream_t st);
+
 cudaError_t launch_ffma(float* out, int blocks, int iters, cudaStream_t st);

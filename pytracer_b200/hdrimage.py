@@ -112,6 +112,29 @@ class HdrImage:
         assert self.valid_coordinates(x, y)
         self._rgb[y, x] = (new_color.r, new_color.g, new_color.b)
 
+    # -- tone mapping on the device (hdrimages.py:120-171; csrc/rt_tonemap.cu)
+    def average_luminosity(self, delta: float = 1e-10) -> float:
+        from . import tonemap
+
+        return tonemap.average_luminosity(self._rgb, delta)
+
+    def normalize_image(self, factor: float, luminosity: Optional[float] = None) -> None:
+        from . import tonemap
+
+        hdr, _, _ = tonemap.tone_map(self._rgb, factor, luminosity, want_ldr=False, flags=tonemap.NORMALIZE)
+        install_array(self, hdr.astype(self._rgb.dtype, copy=False))
+
+    def clamp_image(self) -> None:
+        from . import tonemap
+
+        hdr, _, _ = tonemap.tone_map(self._rgb, want_ldr=False, flags=tonemap.CLAMP)
+        install_array(self, hdr.astype(self._rgb.dtype, copy=False))
+
+    def write_ldr_image(self, stream, format: str, gamma: float = 1.0) -> None:
+        from . import tonemap
+
+        tonemap.write_ldr_image(self, stream, format, gamma=gamma, flags=0)
+
     def write_pfm(self, stream, little_endian: bool = True) -> None:
         stream.write(f"PF\n{self.width} {self.height}\n{'-1.0' if little_endian else '1.0'}\n".encode("ascii"))
         stream.write(self._rgb[::-1].astype("<f4" if little_endian else ">f4").tobytes())

@@ -480,3 +480,85 @@ def test_config5_full_size_properties():
     rgb64, hit64, st64 = sc.render(small, want_hit=True)
     assert np.array_equal(hit64, ref["hit_index"]) and st64["rays_shadow"] == ref["rays_shadow"]
     assert np.allclose(rgb64, ref["rgb"], rtol=1e-9, atol=1e-12)
+
+
+# ------------------------------------------------------------------ tone mapping
+def test_tone_mapping_matches_the_reference_bytes():
+    """hdrimages.py:120-171 on the device: LDR bytes bit-exact against the reference's PNG, average
+    luminosity and normalised values to fp64 / fp32 rounding."""
+    from pytracer_b200 import tonemap
+    from test_oracle_golden import tonemap_cases
+
+    for i, img, factor, lum, gamma, g in tonemap_cases():
+        avg = tonemap.average_luminosity(img)
+        assert abs(avg - float(g[f"case{i}_avg"])) <= 1e-10 * avg  # order of the fp64 sum only
+        hdr, ldr, st = tonemap.tone_map(img, factor, lum, gamma)
+        assert np.array_equal(ldr, g[f"case{i}_ldr"]), f"case {i}: {(ldr != g[f'case{i}_ldr']).sum()} bytes differ"
+        assert np.allclose(hdr, g[f"case{i}_hdr"], rtol=2e-7, atol=1e-45)  # stored as fp32
+        assert abs(st["luminosity"] - (lum if lum else float(g[f"case{i}_avg"]))) <= 1e-10 * st["luminosity"]
+        assert st["n_launches"] == (1 if lum else 2)
+
+
+def test_hdrimage_tone_mapping_methods_mirror_the_reference():
+    # tests/test_all.py:239-268 on the device-backed HdrImage
+    from pytracer_b200.hdrimage import HdrImage
+    from pytracer_b200.scene import Color
+
+    def fresh():
+        img = HdrImage(2, 1)
+        img.set_pixel(0, 0, Color(0.5e1, 1.0e1, 1.5e1))
+        img.set_pixel(1, 0, Color(0.5e3, 1.0e3, 1.5e3))
+        return img
+
+    assert abs(fresh().average_luminosity(delta=0.0) - 100.0) < 1e-9
+    img = fresh()
+    img.normalize_image(factor=1000.0, luminosity=100.0)
+    assert img.get_pixel(0, 0).is_close(Color(0.5e2, 1.0e2, 1.5e2))
+    assert img.get_pixel(1, 0).is_close(Color(0.5e4, 1.0e4, 1.5e4))
+    img = fresh()
+    img.clamp_image()
+    for p in img.pixels:
+        assert 0 <= p.r <= 1 and 0 <= p.g <= 1 and 0 <= p.b <= 1
+    assert abs(img.get_pixel(0, 0).r - 5.0 / 6.0) < 1e-6
+
+
+def test_tone_mapping_full_size_properties_on_device_buffers():
+    """3840x2160 (BASELINE configs 4/5 frame size) on device buffers: the oracle on a window, and
+    size-independent properties — scaling the image scales its average luminosity, a passed-in
+    luminosity gives the same bytes as the computed one, the map is monotonic."""
+    import torch
+
+    from oracle import tonemap_oracle as tm
+    from pytracer_b200 import tonemap
+
+    h, w = 2160, 3840
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    img = torch.exp(torch.randn((h, w, 3), device="cuda", generator=gen) * 2.0).contiguous()
+    n = h * w
+    ldr = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
+    hdr = torch.empty_like(img)
+    st = tonemap.tone_map_device(img.data_ptr(), n, 0.7, None, 1.0, hdr.data_ptr(), ldr.data_ptr())
+    host = img.cpu().numpy()
+    ref_lum = tm.average_luminosity(host)
+    assert abs(st["luminosity"] - ref_lum) <= 1e-10 * ref_lum
+    _, ref_hdr, ref_ldr = tm.tone_map(host[:64], 0.7, st["luminosity"], 1.0)
+    assert np.array_equal(ldr[:64].cpu().numpy(), ref_ldr)
+    assert np.allclose(hdr[:64].cpu().numpy(), ref_hdr, rtol=2e-7)
+    # idempotence: passing the luminosity in skips the first kernel and gives the same bytes
+    ldr2 = torch.empty_like(ldr)
+    st2 = tonemap.tone_map_device(img.data_ptr(), n, 0.7, st["luminosity"], 1.0, 0, ldr2.data_ptr())
+    assert st2["n_launches"] == 1 and torch.equal(ldr, ldr2)
+    # homogeneity (delta = 1e-10 is negligible against exp(N(0, 2)) values)
+    st4 = tonemap.tone_map_device((img * 4.0).contiguous().data_ptr(), n, 0.7, None, 1.0, 0, ldr2.data_ptr())
+    assert abs(st4["luminosity"] / st["luminosity"] - 4.0) < 1e-6
+    assert torch.equal(ldr, ldr2)  # same normalised image -> same bytes
+    # monotonic: brighter input never gives a darker byte
+    order = torch.argsort(img.reshape(-1)[: 1 << 20])
+    b = ldr.reshape(-1)[: 1 << 20][order].to(torch.int16)
+    assert int((b[1:] - b[:-1]).min()) >= 0
+    # a misaligned view takes the scalar path and agrees
+    flat = torch.empty(3 * n + 1, dtype=torch.float32, device="cuda")
+    flat[1:] = img.reshape(-1)
+    ldr3 = torch.empty(3 * n + 1, dtype=torch.uint8, device="cuda")
+    tonemap.tone_map_device(flat.data_ptr() + 4, n, 0.7, st["luminosity"], 1.0, 0, ldr3.data_ptr() + 1)
+    assert torch.equal(ldr3[1:], ldr.reshape(-1))

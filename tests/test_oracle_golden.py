@@ -149,3 +149,29 @@ def test_1080p_config2_bit_exact():
     r = oracle.render(fs, make_params(1920, 1080, cam, "pointlight", 0))
     assert np.array_equal(r["rgb"].astype(np.float32), g["pointlight_rgb_f32"])
     assert [r["rays_closest"], r["rays_shadow"]] == g["pointlight_rays"].tolist() == [2073600, 1589113]
+
+
+# ------------------------------------------------------------------ tone mapping
+def tonemap_cases():
+    g = golden("tonemap.npz")
+    for i in range(int(g["n_cases"])):
+        factor, lum, gamma = (float(x) for x in g[f"case{i}_params"])
+        yield i, g[f"img_{str(g[f'case{i}_image'])}"], factor, (None if np.isnan(lum) else lum), gamma, g
+
+
+def test_tonemap_oracle_matches_the_reference():
+    from oracle import tonemap_oracle as tm
+
+    for i, img, factor, lum, gamma, g in tonemap_cases():
+        avg = tm.average_luminosity(img)
+        assert avg == float(g[f"case{i}_avg"])  # same logs added in the same order
+        used, hdr, ldr = tm.tone_map(img, factor, lum, gamma)
+        assert np.allclose(hdr, g[f"case{i}_hdr"], rtol=1e-15, atol=0)
+        assert np.array_equal(ldr, g[f"case{i}_ldr"])  # bit-exact bytes of the reference's PNG
+    # tests/test_all.py:239-268
+    kat = np.array([[[5.0, 10.0, 15.0], [500.0, 1000.0, 1500.0]]])
+    assert abs(tm.average_luminosity(kat, delta=0.0) - 100.0) < 1e-9
+    assert abs(tm.average_luminosity(kat, delta=0.0) - float(golden("tonemap.npz")["kat_avg_delta0"])) < 1e-12
+    out = tm.normalize_and_clamp(kat, factor=1000.0, luminosity_value=100.0)
+    assert np.allclose(out / (1 - out), [[0.5e2, 1.0e2, 1.5e2], [0.5e4, 1.0e4, 1.5e4]])
+    assert (out >= 0).all() and (out <= 1).all()
