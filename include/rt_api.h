@@ -197,6 +197,14 @@ const char* rt_last_error(void);
 int rt_scene_create(const rt_scene_desc* desc, rt_scene** out);
 void rt_scene_destroy(rt_scene* scene);
 
+/* Animation: new Transformation.m / .invm (double[n][12] each, rows 0..2) for the shapes
+ * [first, first + n) of World.shapes; everything else of the scene stays resident.  Replaces the
+ * reference's per-frame re-parse with `--declare-float clock:VALUE` (main.py:122-128,
+ * scene_file.py:654-675) for frames where only transformations change.  Enqueued on `stream`
+ * (cudaStream_t as void*, NULL = default), after the renders already enqueued there. */
+int rt_scene_update_transforms(rt_scene* scene, int32_t first, int32_t n, const double* m,
+                               const double* invm, void* stream);
+
 /* ---- the hot path: ImageTracer.fire_all_rays(renderer) ---- */
 /* Host buffers: out_rgb float[H][W][3] (or double if out_f64), out_hit_index int32[H][W]
  * (optional; shape hit by the LAST sample of each pixel, -1 = miss). Blocking. */

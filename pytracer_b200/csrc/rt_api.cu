@@ -72,6 +72,10 @@ struct rt_scene {
   DevPigment* pigments = nullptr;
   DevLight* lights = nullptr;
   double* texels64 = nullptr;
+  // host mirrors of the transform tables (sorted order) for rt_scene_update_transforms
+  std::vector<float> h_invm32, h_m32, h_packed;
+  std::vector<double> h_invm64, h_m64;
+  std::vector<int> sorted_of_orig;  // World.shapes index -> sorted index
   std::vector<cudaArray_t> arrays;
   std::vector<cudaTextureObject_t> textures;
   Workspace* ws = nullptr;
@@ -210,6 +214,9 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
   for (int i = s->n_spheres; i < s->n_shapes; ++i)
     for (int k = 0; k < 12; ++k) packed[(size_t)s->n_pairs * 24 + 12 * (size_t)(i - s->n_spheres) + k] = invm32[12 * (size_t)i + k];
   UP(packed32, packed)
+  s->sorted_of_orig.assign(d->n_shapes, 0);
+  for (int j = 0; j < d->n_shapes; ++j) s->sorted_of_orig[orig[j]] = j;
+  s->h_invm32 = invm32; s->h_m32 = m32; s->h_invm64 = invm64; s->h_m64 = m64; s->h_packed = packed;
 
   // ---- textures: fp64 copy for the fp64 path, float4 CUDA arrays behind texture objects for fp32
   std::vector<double> tex64;
@@ -312,6 +319,35 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
   e = cudaMemcpy(s->arena, arena.host.data(), arena.host.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { rt_scene_destroy(s); return fail(RT_ERR_CUDA, "scene upload: %s", cudaGetErrorString(e)); }
   *out = s;
+  return RT_OK;
+}
+
+// Animation (the reference re-parses the scene per frame with `-d clock:VALUE`,
+// scene_file.py:654-675 / main.py:122-128): only Transformation.m / .invm of some shapes change between
+// frames, so the resident scene is patched in place — 336 B per shape over five tables — instead of
+// being rebuilt.  Ordered on `stream` after the renders already enqueued there.
+extern "C" int rt_scene_update_transforms(rt_scene* s, int32_t first, int32_t n, const double* m, const double* invm, void* stream) {
+  if (!s || !m || !invm) return fail(RT_ERR_INVALID, "rt_scene_update_transforms: null argument");
+  if (first < 0 || n < 0 || first + n > s->n_shapes) return fail(RT_ERR_INVALID, "shapes [%d, %d) outside the scene's %d shapes", first, first + n, s->n_shapes);
+  if (n == 0) return RT_OK;
+  CU(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_planes_base = s->n_pairs * 24;
+  for (int i = 0; i < n; ++i) {
+    const int j = s->sorted_of_orig[first + i];
+    for (int k = 0; k < 12; ++k) {
+      const double a = invm[12 * (size_t)i + k], b = m[12 * (size_t)i + k];
+      s->h_invm64[12 * (size_t)j + k] = a; s->h_m64[12 * (size_t)j + k] = b;
+      s->h_invm32[12 * (size_t)j + k] = (float)a; s->h_m32[12 * (size_t)j + k] = (float)b;
+      if (j < s->n_spheres) s->h_packed[(size_t)(j / 2) * 24 + 2 * k + (j & 1)] = (float)a;
+      else s->h_packed[(size_t)n_planes_base + 12 * (size_t)(j - s->n_spheres) + k] = (float)a;
+    }
+  }
+  CU(cudaMemcpyAsync(s->invm32, s->h_invm32.data(), s->h_invm32.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(s->m32, s->h_m32.data(), s->h_m32.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(s->invm64, s->h_invm64.data(), s->h_invm64.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(s->m64, s->h_m64.data(), s->h_m64.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(s->packed32, s->h_packed.data(), s->h_packed.size() * sizeof(float), cudaMemcpyHostToDevice, st));
   return RT_OK;
 }
 

@@ -37,6 +37,25 @@ class DeviceScene:
         except Exception:
             pass
 
+    def update_transforms(self, first: int, m: np.ndarray, invm: np.ndarray, stream: int = 0) -> None:
+        """New Transformation.m / .invm rows 0..2 ((n, 12) fp64 each) for shapes [first, first + n) of
+        World.shapes; the rest of the scene stays resident (animation frames)."""
+        m = np.ascontiguousarray(m, dtype=np.float64).reshape(-1, 12)
+        invm = np.ascontiguousarray(invm, dtype=np.float64).reshape(-1, 12)
+        assert m.shape == invm.shape
+        _native.check(self._lib.rt_scene_update_transforms(self._handle, int(first), m.shape[0], _ptr(m), _ptr(invm),
+                                                           C.c_void_p(stream) if stream else None))
+        self.flat.shape_m.reshape(-1, 12)[first:first + m.shape[0]] = m
+        self.flat.shape_invm.reshape(-1, 12)[first:first + m.shape[0]] = invm
+
+    def update_from_world(self, world, stream: int = 0) -> None:
+        """Same shapes, materials and lights as the resident scene, new transformations (e.g. the next
+        frame of an animation parsed with another `clock`)."""
+        new = world if isinstance(world, FlatScene) else flatten_world(world)
+        if not self.flat.differs_only_in_transforms(new):
+            raise ValueError("update_from_world: more than the transformations changed; build a new DeviceScene")
+        self.update_transforms(0, new.shape_m, new.shape_invm, stream)
+
     # ------------------------------------------------------------------ the hot path
     def render(self, params: _abi.rt_render_params, want_hit: bool = False, out: Optional[np.ndarray] = None,
                replay_states: Optional[np.ndarray] = None) -> Tuple[np.ndarray, Optional[np.ndarray], dict]:

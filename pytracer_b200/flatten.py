@@ -96,6 +96,14 @@ class FlatScene:
         self.desc = d
         return d
 
+    def differs_only_in_transforms(self, other: "FlatScene") -> bool:
+        """True when `other` has the same shapes, materials, pigments, lights and textures and may differ
+        in Transformation.m / .invm only (the next frame of an animation)."""
+        return (np.array_equal(self.shape_kind, other.shape_kind) and np.array_equal(self.shape_material, other.shape_material)
+                and bytes(self.materials) == bytes(other.materials) and bytes(self.pigments) == bytes(other.pigments)
+                and bytes(self.lights) == bytes(other.lights) and self.texels.shape == other.texels.shape
+                and np.array_equal(self.texels, other.texels))
+
     def to_npz_dict(self) -> dict:
         """Portable dump (used for the golden fixtures)."""
         mats = np.array([(m.brdf_kind, m.brdf_pigment, m.emitted_pigment) for m in self.materials], dtype=np.int32).reshape(-1, 3)

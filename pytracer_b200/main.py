@@ -134,5 +134,66 @@ def render(width, height, algorithm, pfm_output, png_output, num_of_rays, max_de
         print(f"PNG output skipped ({e})")
 
 
+@cli.command("animate")
+@click.option("--width", type=int, default=640)
+@click.option("--height", type=int, default=480)
+@click.option("--algorithm", type=click.Choice(RENDERERS), default="pathtracing")
+@click.option("--output-prefix", type=str, default="frame", help="files are <prefix>NNN.pfm / .png")
+@click.option("--num-of-rays", type=int, default=10)
+@click.option("--max-depth", type=int, default=3)
+@click.option("--init-state", type=int, default=45)
+@click.option("--init-seq", type=int, default=54)
+@click.option("--samples-per-pixel", type=int, default=1)
+@click.option("--declare-float", "-d", type=str, multiple=True)
+@click.option("--variable", type=str, default="clock", help="the float variable that changes from frame to frame")
+@click.option("--start", type=float, default=0.0)
+@click.option("--stop", type=float, default=360.0)
+@click.option("--frames", type=int, default=36)
+@click.option("--variant", type=click.Choice(["auto", "mega", "warp"]), default="auto")
+@click.option("--precision", type=click.Choice(["auto", "f32", "f64"]), default="auto")
+@click.option("--parser", type=click.Choice(["auto", "reference", "builtin"]), default="auto")
+@click.option("--no-png", is_flag=True)
+@click.argument("input_scene_name", type=str)
+def animate(width, height, algorithm, output_prefix, num_of_rays, max_depth, init_state, init_seq, samples_per_pixel,
+            declare_float, variable, start, stop, frames, variant, precision, parser, no_png, input_scene_name):
+    """The loop users of the reference write around `render -d clock:VALUE` (one process, one parse and
+    one full render per frame): here the scene stays resident in HBM and only the transformations that
+    changed are uploaded per frame."""
+    samples_per_side = int(sqrt(samples_per_pixel))
+    if samples_per_side ** 2 != samples_per_pixel:
+        print(f"Error, the number of samples per pixel ({samples_per_pixel}) must be a perfect square")
+        return
+    base = build_variable_table(declare_float)
+    renderer, patched = None, 0
+    t_all = perf_counter()
+    for f in range(frames):
+        value = start + (stop - start) * f / max(1, frames)
+        scene = load_scene(input_scene_name, dict(base, **{variable: value}), parser)
+        if renderer is None:
+            extra = dict(variant=variant, precision=precision)
+            renderer = {"onoff": OnOffRenderer, "flat": FlatRenderer, "pointlight": PointLightRenderer}.get(algorithm)
+            if renderer is None:
+                renderer = PathTracer(world=scene.world, pcg=PCG(init_state=init_state, init_seq=init_seq),
+                                      num_of_rays=num_of_rays, max_depth=max_depth, **extra)
+            else:
+                renderer = renderer(world=scene.world, background_color=BLACK, **extra)
+        else:
+            patched += bool(renderer.set_world(scene.world))
+        image = HdrImage(width, height)
+        tracer = CudaImageTracer(image=image, camera=scene.camera, samples_per_side=samples_per_side)
+        t0 = perf_counter()
+        tracer.fire_all_rays(renderer)
+        dt = perf_counter() - t0
+        with open(f"{output_prefix}{f:03d}.pfm", "wb") as outf:
+            image.write_pfm(outf)
+        if not no_png:
+            from .tonemap import write_ldr_image
+
+            with open(f"{output_prefix}{f:03d}.png", "wb") as outf:
+                write_ldr_image(image, outf, "PNG", factor=1.0)
+        print(f"frame {f:03d} ({variable} = {value:g}): rendered in {dt * 1e3:.1f} ms")
+    print(f"{frames} frames in {perf_counter() - t_all:.2f} s; the resident scene was patched in place for {patched} of them")
+
+
 if __name__ == "__main__":
     cli()

@@ -70,6 +70,24 @@ class CudaRenderer(Renderer):
             self._scene.close()
         self._scene = DeviceScene(self.world)
 
+    def set_world(self, world) -> bool:
+        """Next frame of an animation (the reference re-parses the scene with another `clock`,
+        main.py:122-128): if only transformations changed the resident device scene is patched in
+        place (rt_scene_update_transforms), otherwise it is rebuilt.  Returns True when patched."""
+        from .flatten import flatten_world
+
+        self.world = world
+        key = (id(world), len(world.shapes), len(getattr(world, "point_lights", [])))
+        if self._scene is not None:
+            new = flatten_world(world)
+            if self._scene.flat.differs_only_in_transforms(new):
+                self._scene.update_from_world(new)
+                self._scene_key = key
+                return True
+        self.refresh()
+        self._scene_key = key
+        return False
+
     def make_params(self, width: int, height: int, camera, samples_per_side: int = 0, aa_pcg: Optional[PCG] = None,
                     **overrides) -> _abi.rt_render_params:
         kw = dict(

@@ -11,7 +11,7 @@ import pytest
 from oracle import oracle
 from pytracer_b200 import _abi, device, scenes
 from pytracer_b200.device import DeviceScene
-from pytracer_b200.flatten import flatten_world
+from pytracer_b200.flatten import flatten_camera, flatten_world
 from pytracer_b200.params import make_params
 from pytracer_b200.pcg import PCG
 from util import c1_params, demo_flat, golden, luminosity, scene2_flat
@@ -562,3 +562,69 @@ def test_tone_mapping_full_size_properties_on_device_buffers():
     ldr3 = torch.empty(3 * n + 1, dtype=torch.uint8, device="cuda")
     tonemap.tone_map_device(flat.data_ptr() + 4, n, 0.7, st["luminosity"], 1.0, 0, ldr3.data_ptr() + 1)
     assert torch.equal(ldr3[1:], ldr.reshape(-1))
+
+
+# ------------------------------------------------------------------ animation
+def test_transform_updates_equal_a_rebuilt_scene():
+    """rt_scene_update_transforms on a resident scene gives, bit for bit, the images of scenes built
+    from scratch for the same frame (fp64 flat/pointlight + hit index, fp32 tables through the path
+    tracer), on demo.txt's `clock` animation and on a many-sphere scene (packed pair table)."""
+    from pytracer_b200.scene import Transformation, Vec, rotation_z, scaling, translation
+
+    w0, cam = scenes.demo_scene(clock=150.0)
+    resident = DeviceScene(w0)
+    camera = flatten_camera(cam)
+    for clock in (10.0, 275.0):
+        w1, _ = scenes.demo_scene(clock=clock)
+        w1.shapes[2].transformation = translation(Vec(0.3, -0.2, 1.0 + clock / 1000.0)) * scaling(Vec(1.0, 0.7, 1.2))
+        fresh = DeviceScene(w1)
+        resident.update_from_world(w1)
+        for algo in ("flat", "pointlight"):
+            p = make_params(96, 72, camera, algo, 2, aa_pcg=PCG(42, 54))
+            a, ha, _ = resident.render(p, want_hit=True)
+            b, hb, _ = fresh.render(p, want_hit=True)
+            assert np.array_equal(a, b) and np.array_equal(ha, hb), (clock, algo)
+        p = make_params(64, 48, camera, "pathtracing", 2, num_of_rays=3, max_depth=3, rr_limit=2, aa_pcg=PCG(42, 54), pt_pcg=PCG(45, 54))
+        assert np.array_equal(resident.render(p)[0], fresh.render(p)[0]), clock
+        fresh.close()
+    # partial update of a scene with an odd number of spheres and planes in between
+    rs = scenes.random_spheres_scene(37, 7, 3, 10.0)
+    resident = DeviceScene(rs.world)
+    camera = flatten_camera(rs.camera)
+    moved = rs.world.shapes[5:12]
+    for k, shape in enumerate(moved):
+        shape.transformation = translation(Vec(0.1 * k, -0.2, 0.05 * k)) * shape.transformation * rotation_z(10.0 * k)
+    fresh = DeviceScene(rs.world)
+    flat = flatten_world(rs.world)
+    resident.update_transforms(5, flat.shape_m.reshape(-1, 12)[5:12], flat.shape_invm.reshape(-1, 12)[5:12])
+    for algo, prec in (("flat", "f64"), ("flat", "f32"), ("pathtracing", "f32")):
+        p = make_params(80, 45, camera, algo, 1, num_of_rays=2, max_depth=2, aa_pcg=PCG(1, 2), pt_pcg=PCG(3, 4), precision=prec)
+        assert np.array_equal(resident.render(p)[0], fresh.render(p)[0]), (algo, prec)
+    with pytest.raises(Exception):
+        resident.update_transforms(len(rs.world.shapes) - 1, np.zeros((2, 12)), np.zeros((2, 12)))
+
+
+def test_animate_command_patches_the_resident_scene(tmp_path):
+    """`animate` over demo.txt's clock: every frame equals a standalone `render -d clock:VALUE` of the
+    same frame, and frames after the first are patched in place rather than rebuilt."""
+    from click.testing import CliRunner
+
+    from pytracer_b200.hdrimage import read_pfm_image
+    from pytracer_b200.main import cli
+
+    scene_file = tmp_path / "demo.txt"
+    scene_file.write_text(DEMO_TEXT)
+    prefix = str(tmp_path / "f")
+    common = ["--width", "96", "--height", "72", "--algorithm", "pointlight", "--samples-per-pixel", "4", "--parser", "builtin"]
+    res = CliRunner().invoke(cli, ["animate", *common, "--frames", "3", "--start", "0", "--stop", "90", "--output-prefix", prefix,
+                                   str(scene_file)])
+    assert res.exit_code == 0, res.output
+    assert "patched in place for 2 of them" in res.output
+    for f, clock in enumerate((0.0, 30.0, 60.0)):
+        pfm = tmp_path / f"single{f}.pfm"
+        res = CliRunner().invoke(cli, ["render", *common, "-d", f"clock:{clock}", "--pfm-output", str(pfm),
+                                       "--png-output", str(tmp_path / "single.png"), str(scene_file)])
+        assert res.exit_code == 0, res.output
+        with open(pfm, "rb") as a, open(f"{prefix}{f:03d}.pfm", "rb") as b:
+            assert np.array_equal(read_pfm_image(a).rgb_array(), read_pfm_image(b).rgb_array()), f
+        assert (tmp_path / f"f{f:03d}.png").stat().st_size > 100
