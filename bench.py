@@ -263,7 +263,7 @@ def run_ours(args, rank, local_rank, world_size):
 
     world, camera, kw, desc, flops_per_ray = workload(args.workload)
     scene = DeviceScene(world)
-    params = build_params(kw, camera, variant=args.variant, precision=args.precision)
+    params = build_params(kw, camera, variant=args.variant, precision=args.precision, accel=args.accel)
     if world_size > 1:
         params = partition_params(params, rank, world_size)
         if args.partition != "auto":
@@ -323,7 +323,7 @@ def run_ours(args, rank, local_rank, world_size):
     for i in range(args.warmup + args.steps):
         renderer = CudaRenderer(world, algorithm=kw["algorithm"], pcg=PCG(45, 54), num_of_rays=kw.get("num_of_rays", 10),
                                 max_depth=kw.get("max_depth", 10), russian_roulette_limit=kw.get("rr_limit", 3),
-                                variant=args.variant, precision=args.precision)
+                                variant=args.variant, precision=args.precision, accel=args.accel)
         tracer = CudaImageTracer(himg, camera, samples_per_side=kw["samples_per_side"], pcg=PCG(42, 54))
         if comm is not None:
             comm.barrier()
@@ -362,7 +362,7 @@ def run_ours(args, rank, local_rank, world_size):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32" if kw["algorithm"] == "pathtracing" or args.precision == "f32" else "f64", "data": "synthetic",
-        "config": {"workload": desc, "variant": args.variant, "rays_per_step": rays // max(1, args.steps),
+        "config": {"workload": desc, "variant": args.variant, "accel": args.accel, "rays_per_step": rays // max(1, args.steps),
                    "partition": {0: "none", 1: "spp", 2: "rows"}[params.part_mode], "l2": "256 MB buffer zeroed between timed steps",
                    "wall_s_timed_region": wall},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(scene_bytes + len(bytes(params))),
@@ -386,6 +386,8 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "f32", "f64"])
     ap.add_argument("--partition", default="auto", choices=["auto", "spp", "rows"],
                     help="multi-GPU split: strata of every pixel (path tracing default) or interleaved rows")
+    ap.add_argument("--accel", default="none", choices=["none", "bvh"],
+                    help="bvh: sphere hierarchy instead of the reference's loop over all shapes (same image; separately reported mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scale", type=int, default=1, help="divide width and height by this (quick experiments only; "
                     "a scaled run is NOT the benchmark and says so in config)")

@@ -69,6 +69,12 @@ enum { RT_PART_NONE = 0, RT_PART_SPP = 1, RT_PART_ROWS = 2 };
  * pixel — the divergence map of the scene. */
 enum { RT_HIT_SHAPE = 0, RT_HIT_RAY_COUNT = 1 };
 
+/* RT_ACCEL_NONE: the reference's algorithm, a loop over every shape per ray (world.py:55-64); this is
+ * the path the FP32 roofline figures are quoted on.  RT_ACCEL_BVH: a bounding-volume hierarchy over
+ * the spheres skips those whose box the ray misses — identical images (same per-shape tests, same
+ * tie rule, conservative culling), O(log N) instead of O(N) work per ray; reported separately. */
+enum { RT_ACCEL_NONE = 0, RT_ACCEL_BVH = 1 };
+
 enum {
   RT_OK = 0,
   RT_ERR_INVALID = -1,   /* bad argument / unsupported combination */
@@ -160,7 +166,7 @@ typedef struct rt_render_params {
   int32_t precision;
   int32_t out_f64;          /* 1: out_rgb is double[H][W][3] instead of float */
   int32_t hit_mode;         /* what out_hit_index receives: RT_HIT_SHAPE or RT_HIT_RAY_COUNT */
-  int32_t _pad;
+  int32_t accel;            /* RT_ACCEL_*: how World.ray_intersection / is_point_visible find their shapes */
 } rt_render_params;
 
 typedef struct rt_stats {

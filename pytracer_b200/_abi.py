@@ -19,6 +19,7 @@ RT_RNG_STREAMS, RT_RNG_REPLAY = 0, 1
 RT_PART_NONE, RT_PART_SPP, RT_PART_ROWS = 0, 1, 2
 RT_HIT_SHAPE, RT_HIT_RAY_COUNT = 0, 1
 PARTITIONS = {"none": 0, "spp": 1, "rows": 2}
+ACCELS = {"none": 0, "bvh": 1}  # RT_ACCEL_*
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_NO_DEVICE, RT_ERR_OVERFLOW = 0, -1, -2, -3, -4
 
@@ -105,7 +106,7 @@ class rt_render_params(C.Structure):
         ("precision", C.c_int32),
         ("out_f64", C.c_int32),
         ("hit_mode", C.c_int32),
-        ("_pad", C.c_int32),
+        ("accel", C.c_int32),
     ]
 
 

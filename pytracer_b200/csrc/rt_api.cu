@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "rt_launch.h"
+#include "rt_bvh.h"
 
 static thread_local char g_err[512] = "";
 
@@ -76,6 +77,11 @@ struct rt_scene {
   std::vector<float> h_invm32, h_m32, h_packed;
   std::vector<double> h_invm64, h_m64;
   std::vector<int> sorted_of_orig;  // World.shapes index -> sorted index
+  // sphere hierarchy (RT_ACCEL_BVH), built on first use and again after a transform update
+  void* bvh_nodes = nullptr;
+  int32_t* bvh_prims = nullptr;
+  bool bvh_valid = false;
+  int bvh_n_nodes = 0, bvh_n_prims = 0, bvh_depth = 0;
   std::vector<cudaArray_t> arrays;
   std::vector<cudaTextureObject_t> textures;
   Workspace* ws = nullptr;
@@ -131,6 +137,7 @@ template <> SceneView<float> view_of<float>(const rt_scene* s) {
   v.n_shapes = s->n_shapes; v.n_spheres = s->n_spheres; v.n_lights = s->n_lights;
   v.packed = s->packed32; v.n_pairs = s->n_pairs; v._pad = 0;
   v.n_materials = s->n_materials; v.n_pigments = s->n_pigments;
+  v.bvh_nodes = (const float4*)s->bvh_nodes; v.bvh_prims = s->bvh_prims; v.accel = 0; v._pad2 = 0;
   return v;
 }
 template <> SceneView<double> view_of<double>(const rt_scene* s) {
@@ -140,6 +147,7 @@ template <> SceneView<double> view_of<double>(const rt_scene* s) {
   v.n_shapes = s->n_shapes; v.n_spheres = s->n_spheres; v.n_lights = s->n_lights;
   v.packed = nullptr; v.n_pairs = 0; v._pad = 0;
   v.n_materials = s->n_materials; v.n_pigments = s->n_pigments;
+  v.bvh_nodes = (const float4*)s->bvh_nodes; v.bvh_prims = s->bvh_prims; v.accel = 0; v._pad2 = 0;
   return v;
 }
 
@@ -160,6 +168,8 @@ extern "C" void rt_scene_destroy(rt_scene* s) {
   for (auto t : s->textures) cudaDestroyTextureObject(t);
   for (auto a : s->arrays) cudaFreeArray(a);
   cudaFree(s->arena);
+  cudaFree(s->bvh_nodes);
+  cudaFree(s->bvh_prims);
   delete s;
 }
 
@@ -348,6 +358,7 @@ extern "C" int rt_scene_update_transforms(rt_scene* s, int32_t first, int32_t n,
   CU(cudaMemcpyAsync(s->invm64, s->h_invm64.data(), s->h_invm64.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(s->m64, s->h_m64.data(), s->h_m64.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(s->packed32, s->h_packed.data(), s->h_packed.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  s->bvh_valid = false;  // rebuilt by the next render that asks for it
   return RT_OK;
 }
 
@@ -396,6 +407,29 @@ static int ensure(void** ptr, size_t* cap, size_t bytes) {
   return RT_OK;
 }
 
+// Builds (host, rt_bvh.h) and uploads the sphere hierarchy of the scene's current transformations.
+static int ensure_bvh(rt_scene* s, cudaStream_t st) {
+  if (s->bvh_valid) return RT_OK;
+  BvhBuild b = bvh_build(s->h_m64.data(), s->n_spheres);
+  if (b.nodes.empty()) {  // no spheres: one node that is never read (the traversal returns first)
+    b.nodes.push_back(BvhHostNode());
+    b.prims.push_back(0);
+  }
+  if (b.max_depth + 2 > 48) return fail(RT_ERR_INVALID, "sphere hierarchy of depth %d exceeds the traversal stack", b.max_depth);
+  CU(cudaStreamSynchronize(st));  // a render still reading the old tree must finish first
+  cudaFree(s->bvh_nodes); cudaFree(s->bvh_prims);
+  s->bvh_nodes = nullptr; s->bvh_prims = nullptr;
+  CU(cudaMalloc(&s->bvh_nodes, b.nodes.size() * sizeof(BvhHostNode)));
+  CU(cudaMalloc((void**)&s->bvh_prims, b.prims.size() * sizeof(int32_t)));
+  CU(cudaMemcpy(s->bvh_nodes, b.nodes.data(), b.nodes.size() * sizeof(BvhHostNode), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(s->bvh_prims, b.prims.data(), b.prims.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  s->bvh_n_nodes = (int)b.nodes.size();
+  s->bvh_n_prims = (int)b.prims.size();
+  s->bvh_depth = b.max_depth;
+  s->bvh_valid = true;
+  return RT_OK;
+}
+
 extern "C" int rt_render_device(rt_scene* s, const rt_render_params* p, void* d_out_rgb, int32_t* d_out_hit, void* stream) {
   if (!s || !p || !d_out_rgb) return fail(RT_ERR_INVALID, "rt_render_device: null argument");
   CU(cudaSetDevice(s->device));
@@ -434,20 +468,26 @@ extern "C" int rt_render_device(rt_scene* s, const rt_render_params* p, void* d_
     CU(cudaMemsetAsync(d_out_rgb, 0, px * 3 * (a.out_f64 ? sizeof(double) : sizeof(float)), st));
     if (d_out_hit) CU(cudaMemsetAsync(d_out_hit, 0xff, px * sizeof(int32_t), st));
   }
+  if (p->accel != RT_ACCEL_NONE && p->accel != RT_ACCEL_BVH) return fail(RT_ERR_INVALID, "accel %d", p->accel);
+  const int accel = (p->accel == RT_ACCEL_BVH && s->n_spheres > 0) ? RT_ACCEL_BVH : RT_ACCEL_NONE;
+  if (accel == RT_ACCEL_BVH && (rc = ensure_bvh(s, st)) != RT_OK) return rc;
+  SceneView<float> v32 = view_of<float>(s);
+  SceneView<double> v64 = view_of<double>(s);
+  v32.accel = v64.accel = accel;
   s->last_info = {0, 0};
   s->last_precision = precision;
   CU(cudaEventRecord(s->ws->ev0, st));
   cudaError_t e = cudaSuccess;
   const char* why = nullptr;
   if (!pt) {
-    e = precision == RT_PRECISION_F64 ? launch_resolve<double>(view_of<double>(s), a, st, &s->last_info)
-                                      : launch_resolve<float>(view_of<float>(s), a, st, &s->last_info);
+    e = precision == RT_PRECISION_F64 ? launch_resolve<double>(v64, a, st, &s->last_info)
+                                      : launch_resolve<float>(v32, a, st, &s->last_info);
   } else if (variant == RT_VARIANT_MEGA) {
-    e = precision == RT_PRECISION_F64 ? launch_pt_mega<double>(view_of<double>(s), a, st, &s->last_info)
-                                      : launch_pt_mega<float>(view_of<float>(s), a, st, &s->last_info);
+    e = precision == RT_PRECISION_F64 ? launch_pt_mega<double>(v64, a, st, &s->last_info)
+                                      : launch_pt_mega<float>(v32, a, st, &s->last_info);
     if (e == cudaErrorInvalidValue) why = "max_depth > 64 with num_of_rays > 1 is not supported by the mega variant";
   } else {
-    e = launch_pt_warp(view_of<float>(s), a, st, s->sm_count, &s->last_info, &why);
+    e = launch_pt_warp(v32, a, st, s->sm_count, &s->last_info, &why, s->bvh_n_nodes, s->bvh_n_prims, s->bvh_depth);
   }
   if (e != cudaSuccess) return fail(why ? RT_ERR_INVALID : RT_ERR_CUDA, "render launch: %s", why ? why : cudaGetErrorString(e));
   CU(cudaEventRecord(s->ws->ev1, st));

@@ -54,6 +54,10 @@ template <typename T> struct SceneView {
   const float* packed;
   int32_t n_pairs, _pad;
   int32_t n_materials, n_pigments;
+  // sphere hierarchy (rt_bvh.cuh), used when accel != 0
+  const float4* bvh_nodes;
+  const int32_t* bvh_prims;
+  int32_t accel, _pad2;
 };
 
 template <typename T> struct Hit {

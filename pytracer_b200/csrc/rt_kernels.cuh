@@ -10,6 +10,7 @@
 //   k_probe     one-item-per-thread / one-stream probes behind the known-answer entry points.
 #pragma once
 #include "rt_launch.h"
+#include "rt_bvh.cuh"
 
 #define RT_RESOLVE_THREADS 256
 #define RT_MEGA_THREADS 128
@@ -151,7 +152,9 @@ k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
   const long long pix = (long long)row * a.width + col;
   const int S2 = a.S > 0 ? a.S * a.S : 1;
 
-  if (F32) {
+  const bool bvh = sc.accel != 0;  // hierarchy traversal: nothing is staged, every thread walks the tree
+  if (bvh) {
+  } else if (F32) {
     if (planes_smem) stage_bytes(sh_planes, planes_g, (size_t)n_planes * 48);
     if (single) stage_bytes(sh_pairs, sc.packed, (size_t)sc.n_pairs * 96);
     __syncthreads();
@@ -175,7 +178,9 @@ k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
     // ---- closest hit: all threads of the block sweep the shape chunks together
     T best_t = Num<T>::inf();
     int best = -1;
-    if constexpr (F32) {
+    if (bvh) {
+      if (mine) closest_bvh<T>(sc, ray, best_t, best);
+    } else if constexpr (F32) {
       int cand[RT_CAND_CAP];
       int nc = 0;
       PackedRay pr;
@@ -228,7 +233,9 @@ k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
         Ray<T> sr;
         if (need) { sr = shadow_ray<T>(load3<T>(sc.lights[l].pos), h.point); ++n_shadow; }
         bool blocked = false;
-        if constexpr (F32) {
+        if (bvh) {
+          if (need) blocked = any_bvh<T>(sc, sr);
+        } else if constexpr (F32) {
           int cand[RT_CAND_CAP];
           int nc = 0;
           PackedRay pr;
@@ -286,7 +293,7 @@ cudaError_t launch_resolve_generic(const SceneView<T>& sc, const RenderArgs& a, 
   const int n_units = F32 ? sc.n_pairs : sc.n_shapes;
   const size_t planes_bytes = (F32 && n_planes <= RT_PLANES_SMEM_MAX) ? (size_t)n_planes * 48 : 0;
   int chunk = (size_t)n_units * unit <= 2 * RT_SMEM_SHAPE_BYTES ? (n_units > 0 ? n_units : 1) : (int)(RT_SMEM_SHAPE_BYTES / unit);
-  size_t smem = planes_bytes + (size_t)chunk * unit;
+  size_t smem = sc.accel ? 16 : planes_bytes + (size_t)chunk * unit;
   long long blocks = (pm.n_pixels + RT_RESOLVE_THREADS - 1) / RT_RESOLVE_THREADS;
   k_resolve<T><<<(unsigned)blocks, RT_RESOLVE_THREADS, smem, st>>>(sc, a, chunk);
   if (info) { info->n_launches += 1; info->variant = 0; }
@@ -311,7 +318,8 @@ template <typename T>
 RT_DEV bool trace_closest(const SceneView<T>& sc, const ScanSrc<T>& src, const Ray<T>& r, Hit<T>& h, int origin = -1) {
   T best_t = Num<T>::inf();
   int best = -1;
-  closest_all<T>(sc, src, r, best_t, best, origin);
+  if (sc.accel) closest_bvh<T>(sc, r, best_t, best, origin);
+  else closest_all<T>(sc, src, r, best_t, best, origin);
   h.idx = -1;
   if (best < 0) return false;
   finish_hit<T>(sc, r, best_t, best, h);

@@ -1,6 +1,9 @@
 // rt_kernels_f32.cu — float instantiations (multiply-add fusion allowed) + the warp-cooperative
 // path tracer, which exists in fp32 only.
+#include <cstdlib>
+
 #include "rt_warp.cuh"
+#include "rt_warp_bvh.cuh"
 #include "rt_resolve_f32.cuh"
 
 template <> cudaError_t launch_resolve<float>(const SceneView<float>& sc, const RenderArgs& a, cudaStream_t st, LaunchInfo* info) {
@@ -10,7 +13,8 @@ template cudaError_t launch_pt_mega<float>(const SceneView<float>&, const Render
 template cudaError_t launch_probe<float>(const SceneView<float>&, const RenderArgs&, const ProbeArgs&, cudaStream_t);
 
 cudaError_t launch_pt_warp(const SceneView<float>& sc, const RenderArgs& a, cudaStream_t st, int sm_count,
-                           LaunchInfo* info, const char** why_not) {
+                           LaunchInfo* info, const char** why_not, int n_nodes, int n_prims, int tree_depth) {
+  if (sc.accel) return launch_pt_warp_bvh(sc, a, st, sm_count, info, why_not, n_nodes, n_prims, tree_depth);  // sphere hierarchy: its own schedule
   return launch_pt_warp_impl(sc, a, st, sm_count, info, why_not);
 }
 

@@ -30,7 +30,9 @@ struct LaunchInfo {
 template <typename T> cudaError_t launch_resolve(const SceneView<T>& sc, const RenderArgs& a, cudaStream_t st, LaunchInfo* info);
 template <typename T> cudaError_t launch_pt_mega(const SceneView<T>& sc, const RenderArgs& a, cudaStream_t st, LaunchInfo* info);
 // fp32 only (rt_kernels_f32.cu): the warp-cooperative wavefront path tracer
-cudaError_t launch_pt_warp(const SceneView<float>& sc, const RenderArgs& a, cudaStream_t st, int sm_count, LaunchInfo* info, const char** why_not);
+// (n_nodes / n_prims / tree_depth describe the sphere hierarchy and are read only when sc.accel != 0)
+cudaError_t launch_pt_warp(const SceneView<float>& sc, const RenderArgs& a, cudaStream_t st, int sm_count, LaunchInfo* info, const char** why_not,
+                           int n_nodes, int n_prims, int tree_depth);
 
 // single-stream probes behind rt_trace_rays / rt_intersect / ... (n items, one thread walks them
 // in order when a PCG stream is shared, otherwise one thread per item)

@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(RT_RESOLVE_THREADS, 2)
 k_resolve_f32(const __grid_constant__ SceneView<float> sc, const __grid_constant__ RenderArgs a, const int chunk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n_planes = sc.n_shapes - sc.n_spheres;
-  const bool single = sc.n_pairs <= chunk;
+  const bool bvh = sc.accel != 0;  // sphere hierarchy (rt_bvh.cuh): no pair staging, every thread walks the tree
+  const bool single = bvh || sc.n_pairs <= chunk;
   const bool planes_smem = n_planes <= RT_PLANES_SMEM_MAX;
   const float* planes_g = sc.packed + 24 * (size_t)sc.n_pairs;
   float* sh_planes = reinterpret_cast<float*>(smem_raw);
@@ -65,7 +66,7 @@ k_resolve_f32(const __grid_constant__ SceneView<float> sc, const __grid_constant
   }
   if (planes_smem) stage_bytes(sh_planes, planes_g, (size_t)n_planes * 48);
   __syncthreads();
-  if (single && sc.n_pairs > 0) {  // the whole pair list, once, by the copy engine
+  if (single && sc.n_pairs > 0 && !bvh) {  // the whole pair list, once, by the copy engine
     if (threadIdx.x == 0) {
       mbar_arrive_expect_tx(&bars[0], (uint32_t)sc.n_pairs * 96u);
       tma_load_1d(buf[0], sc.packed, (uint32_t)sc.n_pairs * 96u, &bars[0]);
@@ -124,14 +125,16 @@ k_resolve_f32(const __grid_constant__ SceneView<float> sc, const __grid_constant
     q0.nc = q1.nc = 0;
     q0.best = q1.best = -1;
     q0.best_t = q1.best_t = Num<float>::inf();
-    sweep(two, q0.mine, q1.mine, q0.ray, q1.ray, q0.cand, q0.nc, q1.cand, q1.nc);
+    if (!bvh) sweep(two, q0.mine, q1.mine, q0.ray, q1.ray, q0.cand, q0.nc, q1.cand, q1.nc);
     if (q0.mine) {
-      resolve_candidates(sc.invm, sc.n_spheres, q0.cand, q0.nc, q0.ray, q0.best_t, q0.best);
+      if (bvh) bvh_closest_spheres<float>(sc, q0.ray, q0.best_t, q0.best, -1);
+      else resolve_candidates(sc.invm, sc.n_spheres, q0.cand, q0.nc, q0.ray, q0.best_t, q0.best);
       scan_plane_block(planes, sc.n_spheres, n_planes, sc.orig, q0.ray, q0.best_t, q0.best);
       ++n_closest; ++n_samples;
     }
     if (q1.mine) {
-      resolve_candidates(sc.invm, sc.n_spheres, q1.cand, q1.nc, q1.ray, q1.best_t, q1.best);
+      if (bvh) bvh_closest_spheres<float>(sc, q1.ray, q1.best_t, q1.best, -1);
+      else resolve_candidates(sc.invm, sc.n_spheres, q1.cand, q1.nc, q1.ray, q1.best_t, q1.best);
       scan_plane_block(planes, sc.n_spheres, n_planes, sc.orig, q1.ray, q1.best_t, q1.best);
       ++n_closest; ++n_samples;
     }
@@ -152,9 +155,14 @@ k_resolve_f32(const __grid_constant__ SceneView<float> sc, const __grid_constant
         const bool go0 = need0 && !blocked0, go1 = need1 && !blocked1;
         int c0[RT_CAND_CAP], c1[RT_CAND_CAP];
         int m0 = 0, m1 = 0;
-        if (single || __syncthreads_or(go0 || go1)) sweep(two, go0, go1, s0, s1, c0, m0, c1, m1);
-        if (go0) blocked0 = any_candidate_blocks(sc.invm, sc.n_spheres, c0, m0, s0);
-        if (go1) blocked1 = any_candidate_blocks(sc.invm, sc.n_spheres, c1, m1, s1);
+        if (bvh) {
+          if (go0) blocked0 = bvh_any_sphere<float>(sc, s0);
+          if (go1) blocked1 = bvh_any_sphere<float>(sc, s1);
+        } else {
+          if (single || __syncthreads_or(go0 || go1)) sweep(two, go0, go1, s0, s1, c0, m0, c1, m1);
+          if (go0) blocked0 = any_candidate_blocks(sc.invm, sc.n_spheres, c0, m0, s0);
+          if (go1) blocked1 = any_candidate_blocks(sc.invm, sc.n_spheres, c1, m1, s1);
+        }
         if (need0 && !blocked0) q0.color = q0.color + light_term<float>(sc, q0.h, q0.ray.d, l);
         if (need1 && !blocked1) q1.color = q1.color + light_term<float>(sc, q1.h, q1.ray.d, l);
       }
@@ -181,7 +189,8 @@ inline cudaError_t launch_resolve_f32(const SceneView<float>& sc, const RenderAr
   const size_t planes_bytes = n_planes <= RT_PLANES_SMEM_MAX ? (size_t)n_planes * 48 : 0;
   // everything in one chunk while it fits 96 KB of shared memory, else 48 KB chunks (512 pairs)
   int chunk = (size_t)sc.n_pairs * 96 <= 2 * RT_SMEM_SHAPE_BYTES ? (sc.n_pairs > 0 ? sc.n_pairs : 1) : RT_SMEM_SHAPE_BYTES / 96;
-  const bool single = sc.n_pairs <= chunk;
+  if (sc.accel) chunk = 1;  // hierarchy traversal: only the plane block and the (unused) barriers
+  const bool single = sc.n_pairs <= chunk || sc.accel;
   size_t smem = planes_bytes + (size_t)chunk * 96 * (single ? 1 : 2) + 16;  // + two mbarriers
   long long blocks = (pm.n_pixels + RT_RESOLVE_THREADS - 1) / RT_RESOLVE_THREADS;
   k_resolve_f32<<<(unsigned)blocks, RT_RESOLVE_THREADS, smem, st>>>(sc, a, chunk);

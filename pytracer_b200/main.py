@@ -79,9 +79,10 @@ def cli():
 @click.option("--variant", type=click.Choice(["auto", "mega", "warp"]), default="auto")
 @click.option("--precision", type=click.Choice(["auto", "f32", "f64"]), default="auto")
 @click.option("--parser", type=click.Choice(["auto", "reference", "builtin"]), default="auto")
+@click.option("--accel", type=click.Choice(["none", "bvh"]), default="none", help="bvh: sphere hierarchy, same image")
 @click.argument("input_scene_name", type=str)
 def render(width, height, algorithm, pfm_output, png_output, num_of_rays, max_depth, init_state, init_seq,
-           samples_per_pixel, declare_float, variant, precision, parser, input_scene_name):
+           samples_per_pixel, declare_float, variant, precision, parser, accel, input_scene_name):
     samples_per_side = int(sqrt(samples_per_pixel))
     if samples_per_side ** 2 != samples_per_pixel:
         print(f"Error, the number of samples per pixel ({samples_per_pixel}) must be a perfect square")
@@ -90,7 +91,7 @@ def render(width, height, algorithm, pfm_output, png_output, num_of_rays, max_de
     image = HdrImage(width, height)
     print(f"Generating a {width}×{height} image")
     tracer = CudaImageTracer(image=image, camera=scene.camera, samples_per_side=samples_per_side)
-    extra = dict(variant=variant, precision=precision)
+    extra = dict(variant=variant, precision=precision, accel=accel)
     if algorithm == "onoff":
         print("Using on/off renderer")
         renderer = OnOffRenderer(world=scene.world, background_color=BLACK, **extra)

@@ -38,6 +38,7 @@ def make_params(
     precision="auto",
     out_f64: bool = False,
     hit_mode: int = _abi.RT_HIT_SHAPE,
+    accel="none",
 ) -> _abi.rt_render_params:
     p = _abi.rt_render_params()
     p.width, p.height, p.samples_per_side = int(width), int(height), int(samples_per_side)
@@ -58,4 +59,5 @@ def make_params(
     p.precision = _abi.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
     p.out_f64 = 1 if out_f64 else 0
     p.hit_mode = hit_mode
+    p.accel = _abi.ACCELS[accel] if isinstance(accel, str) else int(accel)
     return p

@@ -39,7 +39,7 @@ class CudaRenderer(Renderer):
     def __init__(self, world, background_color: Color = BLACK, algorithm: str = "pathtracing",
                  pcg: Optional[PCG] = None, num_of_rays: int = 10, max_depth: int = 10,
                  russian_roulette_limit: int = 3, ambient_color: Color = None, color: Color = WHITE,
-                 variant: str = "auto", precision: str = "auto"):
+                 variant: str = "auto", precision: str = "auto", accel: str = "none"):
         super().__init__(world, background_color)
         if algorithm not in RENDERERS:
             raise ValueError(f"Unknown renderer: {algorithm}")
@@ -52,6 +52,7 @@ class CudaRenderer(Renderer):
         self.color = color
         self.variant = variant
         self.precision = precision
+        self.accel = accel  # "none": the reference's loop over all shapes; "bvh": sphere hierarchy (same image)
         self.last_stats: dict = {}
         self._scene: Optional[DeviceScene] = None
         self._scene_key = None
@@ -94,7 +95,7 @@ class CudaRenderer(Renderer):
             algorithm=self.algorithm, samples_per_side=samples_per_side, background=self.background_color,
             onoff_color=self.color, ambient=self.ambient_color, num_of_rays=self.num_of_rays,
             max_depth=self.max_depth, rr_limit=self.russian_roulette_limit, aa_pcg=aa_pcg, pt_pcg=self.pcg,
-            variant=self.variant, precision=self.precision,
+            variant=self.variant, precision=self.precision, accel=self.accel,
         )
         kw.update(overrides)
         return make_params(width, height, camera, **kw)

@@ -628,3 +628,81 @@ def test_animate_command_patches_the_resident_scene(tmp_path):
         with open(pfm, "rb") as a, open(f"{prefix}{f:03d}.pfm", "rb") as b:
             assert np.array_equal(read_pfm_image(a).rgb_array(), read_pfm_image(b).rgb_array()), f
         assert (tmp_path / f"f{f:03d}.png").stat().st_size > 100
+
+
+# ------------------------------------------------------------------ sphere hierarchy
+@pytest.mark.parametrize("n_spheres", [1, 3, 37, 1100])
+def test_bvh_images_equal_the_linear_scan(n_spheres):
+    """accel="bvh" must give the images of the default loop over all shapes (same per-shape tests, same
+    tie rule, conservative culling): BIT FOR BIT in fp64 — every renderer, and still equal to the
+    oracle's plain loop.  In fp32 the two may differ on a handful of rays, and there the tree is the more
+    faithful one: for a ray that starts thousands of units away (the ground near the horizon) the fp32
+    discriminant of a far sphere is rounding noise (|o'|^2 ~ 1e8 against a radius of 1), so the scan
+    reports phantom hits on spheres the ray passes at a distance; the tree never tests a sphere whose
+    box the ray misses.  Bar for fp32: <= 0.1 % of pixels differ."""
+    rs = scenes.random_spheres_scene(n_spheres, 2024, 4, 20.0, with_light=True)
+    fs = flatten_world(rs.world)
+    sc = DeviceScene(fs)
+    w, h = (96, 54) if n_spheres > 100 else (64, 36)
+    for algo in ("onoff", "flat", "pointlight"):
+        for prec in ("f64", "f32"):
+            kw = dict(precision=prec, out_f64=(prec == "f64"), aa_pcg=PCG(42, 54))
+            a, ha, sa = sc.render(make_params(w, h, rs.camera, algo, 2, **kw), want_hit=True)
+            b, hb, sb = sc.render(make_params(w, h, rs.camera, algo, 2, accel="bvh", **kw), want_hit=True)
+            assert sa["rays_closest"] == sb["rays_closest"]
+            if prec == "f64":
+                assert np.array_equal(ha, hb) and np.array_equal(a, b), algo
+                assert sa["rays_shadow"] == sb["rays_shadow"]
+            else:
+                assert (ha != hb).mean() <= 1e-3 and (a != b).any(axis=-1).mean() <= 1e-3, algo
+    ref = oracle.render(fs, make_params(w, h, rs.camera, "pointlight", 0, out_f64=True))
+    rgb, hit, st = sc.render(make_params(w, h, rs.camera, "pointlight", 0, out_f64=True, accel="bvh"), want_hit=True)
+    assert np.array_equal(hit, ref["hit_index"]) and st["rays_shadow"] == ref["rays_shadow"]
+    assert np.allclose(rgb, ref["rgb"], rtol=1e-9, atol=1e-12)
+    # path tracing: fp64 megakernel bit for bit (same streams, same tree); fp32 kernels within the bar above
+    kw = dict(algorithm="pathtracing", samples_per_side=2, num_of_rays=3, max_depth=3, rr_limit=2,
+              aa_pcg=PCG(42, 54), pt_pcg=PCG(45, 54), hit_mode=_abi.RT_HIT_RAY_COUNT)
+    a, ca, sa = sc.render(make_params(w, h, rs.camera, variant="mega", precision="f64", out_f64=True, **kw), want_hit=True)
+    b, cb, sb = sc.render(make_params(w, h, rs.camera, variant="mega", precision="f64", out_f64=True, accel="bvh", **kw), want_hit=True)
+    assert np.array_equal(ca, cb) and np.array_equal(a, b) and sa["rays_closest"] == sb["rays_closest"]
+    for variant in ("warp", "mega"):
+        a, ca, sa = sc.render(make_params(w, h, rs.camera, variant=variant, **kw), want_hit=True)
+        b, cb, sb = sc.render(make_params(w, h, rs.camera, variant=variant, accel="bvh", **kw), want_hit=True)
+        assert sb["overflow"] == 0
+        assert (ca != cb).mean() <= 2e-3, variant  # the same ray tree, pixel by pixel
+        same = ca == cb
+        # (the warp kernel adds a pixel's contributions in lane order, which differs between the modes)
+        assert np.allclose(a[same], b[same], rtol=2e-5, atol=1e-6) or variant == "mega"
+        assert abs(luminosity(a).mean() - luminosity(b).mean()) <= 2e-3 * luminosity(a).mean()
+
+
+def test_bvh_follows_transform_updates_and_full_size_config5():
+    """The hierarchy is rebuilt after rt_scene_update_transforms; BASELINE config 5 at full size
+    (3840x2160, 4 spp, 4096 ellipsoids, point light): bvh == linear scan on all 8.3 M pixels."""
+    from pytracer_b200.scene import Vec, translation
+
+    rs = scenes.random_spheres_scene(64, 5, 6, 8.0, with_light=True)
+    sc = DeviceScene(rs.world)
+    p_lin = make_params(80, 45, rs.camera, "flat", 0, precision="f32")
+    p_bvh = make_params(80, 45, rs.camera, "flat", 0, precision="f32", accel="bvh")
+    assert (sc.render(p_lin)[0] != sc.render(p_bvh)[0]).any(axis=-1).mean() <= 1e-3
+    for shape in rs.world.shapes[:40]:
+        shape.transformation = translation(Vec(1.5, -2.0, 0.5)) * shape.transformation
+    sc.update_from_world(rs.world)
+    moved = sc.render(p_bvh)[0]
+    assert (moved != sc.render(p_lin)[0]).any(axis=-1).mean() <= 1e-3
+    assert np.array_equal(moved, DeviceScene(rs.world).render(p_bvh)[0])
+
+    rs = scenes.random_spheres_scene(4096, 2025, 5, 40.0, with_light=True)
+    sc = DeviceScene(rs.world)
+    kw = dict(precision="f32", aa_pcg=PCG(42, 54))
+    a, ha, sa = sc.render(make_params(3840, 2160, rs.camera, "pointlight", 2, **kw), want_hit=True)
+    b, hb, sb = sc.render(make_params(3840, 2160, rs.camera, "pointlight", 2, accel="bvh", **kw), want_hit=True)
+    assert sa["rays_closest"] == sb["rays_closest"]
+    assert (ha != hb).mean() <= 1e-4 and (a != b).any(axis=-1).mean() <= 1e-3  # fp32: see the test above
+    assert sb["kernel_ms"] < sa["kernel_ms"]
+    # fp64, the bit-faithful default of this renderer: a window of the same frame, bit for bit
+    kw = dict(precision="f64", out_f64=True, aa_pcg=PCG(42, 54))
+    a, ha, sa = sc.render(make_params(384, 216, rs.camera, "pointlight", 2, **kw), want_hit=True)
+    b, hb, sb = sc.render(make_params(384, 216, rs.camera, "pointlight", 2, accel="bvh", **kw), want_hit=True)
+    assert np.array_equal(ha, hb) and np.array_equal(a, b) and sa["rays_shadow"] == sb["rays_shadow"]
