@@ -25,6 +25,11 @@ import sys
 import tempfile
 import time
 
+# rank 0 prints exactly ONE line on stdout (the JSON): NCCL's own "NCCL version ..." banner (printed at
+# NCCL_DEBUG=VERSION and above) would be a second one
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -403,6 +408,11 @@ def main():
         run_reference(args, rank, world_size)
     else:
         run_ours(args, rank, local_rank, world_size)
+        if world_size > 1:
+            import torch.distributed as dist
+
+            if dist.is_initialized():
+                dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -438,14 +438,16 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   if (a.max_depth >= 1023) { *why_not = "max_depth >= 1023 is not supported by the warp variant (use mega)"; return cudaErrorInvalidValue; }
   WarpCfg cfg;
   cfg.per_pixel = L;
-  // Samples per task.  Scenes whose shape block is tiny (demo.txt) take tasks of >= 64 samples (fewer
-  // partially filled iterations per sample); scenes that fill shared memory with shapes keep one
-  // warp-full per task so that two CTAs still fit an SM.
+  // Samples per task: all strata of one pixel when there are at least 32 of them (demo.txt at 64 spp:
+  // 64-sample tasks, lane-private sums), otherwise as many pixels as make one warp-full of samples.
   size_t shape_bytes = (size_t)sc.n_pairs * 96 + (size_t)(sc.n_shapes - sc.n_spheres) * 48;
   const bool shapes_smem = shape_bytes > 0 && shape_bytes <= 64 * 1024;
   const bool small = sc.n_shapes > 0 && sc.n_spheres <= RT_SMALL_MAX_SPHERES && sc.n_shapes <= RT_SMALL_MAX_SHAPES &&
                      sc.n_materials <= RT_SMALL_MAX_MATERIALS && sc.n_pigments <= RT_SMALL_MAX_PIGMENTS;
-  const int want = small ? 64 : 32;
+  // (multi-pixel tasks, L < 32: 32 samples per task keep the accumulator columns small enough for three
+  // resident blocks per SM — measured on demo.txt split over 8 GPUs: 50.9 vs 41.4 Grays/s per GPU)
+  int want = 32;
+  if (const char* env = getenv("RT_WARP_WANT")) want = atoi(env);  // tuning aid: samples per task
   if (L >= 32) cfg.group = 1;
   else if (L >= 4) cfg.group = (want + L - 1) / L < RT_ACC_LANES_MAX_GROUP ? (want + L - 1) / L : RT_ACC_LANES_MAX_GROUP;
   else cfg.group = 32 / L;
@@ -458,16 +460,31 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   const long long prims = (long long)cfg.rounds * 32;
   long long cap = a.num_of_rays == 1 ? prims + 32 : prims + 32ll * (long long)a.max_depth;
   if (cap < 64) cap = 64;
-  const int acc_mode = cfg.group == 1 ? ACC_REG : (cfg.group <= RT_ACC_LANES_MAX_GROUP ? ACC_LANES : ACC_SEG);
+  int acc_mode = cfg.group == 1 ? ACC_REG : (cfg.group <= RT_ACC_LANES_MAX_GROUP ? ACC_LANES : ACC_SEG);
   cfg.shape_bytes = small ? (int)SM_BYTES : (shapes_smem ? (int)((shape_bytes + 15) / 16 * 16) : 0);
   const size_t limit = 200 * 1024;
   int warps = (small ? RT_SMALL_THREADS : RT_WARP_MAX_THREADS) / 32;
   size_t per_warp = 0, smem = 0;
+  auto footprint = [&](int mode, int w, size_t& pw) {
+    pw = (size_t)(cap + 1) * sizeof(ScatterRec);
+    if (mode == ACC_SEG) pw += 32 * sizeof(int) + 96 * sizeof(float);
+    if (mode == ACC_LANES) pw += 32 * sizeof(int) + (size_t)cfg.group * 96 * sizeof(float);
+    return cfg.shape_bytes + pw * w;
+  };
+  // The accumulator columns of ACC_LANES cost 384 B per pixel and warp; where that takes a resident
+  // block away from the SM (demo.txt split over 4 or 8 GPUs: 2 blocks instead of 3, -25 % throughput)
+  // the segmented-scan accumulators (ACC_SEG, 512 B per warp in all) are the better trade.
+  if (acc_mode == ACC_LANES) {
+    size_t pw_l, pw_s;
+    const size_t sm_bytes = 227 * 1024;
+    const size_t blocks_lanes = sm_bytes / (footprint(ACC_LANES, warps, pw_l) + 1024);
+    const size_t blocks_seg = sm_bytes / (footprint(ACC_SEG, warps, pw_s) + 1024);
+    const size_t by_threads = 2048 / (warps * 32), by_regs = small ? RT_SMALL_MINB : 2;
+    if (std::min(std::min(blocks_seg, by_threads), by_regs) > std::min(std::min(blocks_lanes, by_threads), by_regs)) acc_mode = ACC_SEG;
+    if (const char* env = getenv("RT_WARP_ACC")) acc_mode = atoi(env);  // tuning aid
+  }
   for (;; warps >>= 1) {
-    per_warp = (size_t)(cap + 1) * sizeof(ScatterRec);
-    if (acc_mode == ACC_SEG) per_warp += 32 * sizeof(int) + 96 * sizeof(float);
-    if (acc_mode == ACC_LANES) per_warp += 32 * sizeof(int) + (size_t)cfg.group * 96 * sizeof(float);
-    smem = cfg.shape_bytes + per_warp * warps;
+    smem = footprint(acc_mode, warps, per_warp);
     if (smem <= limit || warps == 1) break;
   }
   if (smem > limit) { *why_not = "max_depth needs a deeper work stack than shared memory holds"; return cudaErrorInvalidValue; }
