@@ -354,15 +354,24 @@ def run_ours(args, rank, local_rank, world_size):
     achieved_tf = rays_per_launch_rank * flops_per_ray / (k_ms * 1e-3) / 1e12
     prop = torch.cuda.get_device_properties(local_rank)
     nominal_tf = prop.multi_processor_count * 128 * 2 * 1.965e9 / 1e12
-    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+    traffic, issue_busy = None, None  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload if SCALE == 1 and world_size == 1 else "")
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if SCALE == 1 and world_size == 1 and args.accel == "none":
+            traffic = prof.get(args.workload)
+            issue_busy = prof.get(args.workload + "_issue_slots_busy")
     except Exception:
         pass
     roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "traffic": traffic, "peak_source": "FFMA micro-benchmark run in this job (rt_bench_ffma); MEASURED_PEAKS.json holds "
                 "only HBM and bf16-tensor peaks, neither bounds this path", "peak_nominal": nominal_tf,
                 "flops_per_ray": flops_per_ray, "kernel_ms": k_ms, "rays_per_launch": rays_per_launch_rank}
+    if issue_busy is not None:  # demo.txt is 184 flop/ray by construction: the resource that binds it is the issue port
+        roofline["issue_slots_busy"] = issue_busy
+        roofline["issue_slots_source"] = "smsp__issue_active.avg.pct_of_peak_sustained_active, profiles/traffic.json (committed ncu capture)"
+    if args.accel != "none":
+        roofline["note"] = ("flops_per_ray is the linear scan's (the reference's algorithm); the hierarchy skips most of that work, "
+                            "so `frac` is a speed-up over the roofline of the linear scan, not a utilisation")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
