@@ -25,10 +25,17 @@ import sys
 import tempfile
 import time
 
-# rank 0 prints exactly ONE line on stdout (the JSON): NCCL's own "NCCL version ..." banner (printed at
-# NCCL_DEBUG=VERSION and above) would be a second one
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# Rank 0 prints exactly ONE line on stdout: the JSON.  Libraries write there too (NCCL prints its
+# "NCCL version ..." banner on fd 1 whenever NCCL_DEBUG is set), so fd 1 is pointed at stderr for the
+# whole run and the JSON line goes to the saved descriptor.
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -180,7 +187,7 @@ def run_reference(args, rank, world_size):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_tonemap(args, rank, local_rank, world_size):
@@ -246,7 +253,7 @@ def run_tonemap(args, rank, local_rank, world_size):
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": host.shape[0] * w / dt, "unit": "pixels/s", "cores": 1, "kind": "port",
                                 "sample": f"{w}x{host.shape[0]} rows of the same frame through oracle/tonemap_oracle.py ({dt:.1f} s)"}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args, rank, local_rank, world_size):
@@ -386,7 +393,7 @@ def run_ours(args, rank, local_rank, world_size):
     if world_size == 1 and not args.no_cpu_baseline:
         v, sample = cpu_baseline_sample(world, camera, kw, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
