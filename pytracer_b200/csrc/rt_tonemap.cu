@@ -103,7 +103,9 @@ k_lum_sum(const float* __restrict__ rgb, long long n_pixels, double delta, doubl
   const long long n_groups = n_pixels / 4;  // 4 pixels = 12 floats = three 16-byte loads
   const float4* v = reinterpret_cast<const float4*>(rgb);
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += (long long)gridDim.x * blockDim.x) {
-    const float4 a = ld_stream(v + 3 * g), b = ld_stream(v + 3 * g + 1), c = ld_stream(v + 3 * g + 2);
+    // default caching, not evict-first: a frame that fits the 126 MB L2 (up to 3840x2160) is still there
+    // when the map kernel reads it next
+    const float4 a = __ldg(v + 3 * g), b = __ldg(v + 3 * g + 1), c = __ldg(v + 3 * g + 2);
     add_pixel(acc, delta, a.x, a.y, a.z);
     add_pixel(acc, delta, a.w, b.x, b.y);
     add_pixel(acc, delta, b.z, b.w, c.x);

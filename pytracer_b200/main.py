@@ -80,9 +80,22 @@ def cli():
 @click.option("--precision", type=click.Choice(["auto", "f32", "f64"]), default="auto")
 @click.option("--parser", type=click.Choice(["auto", "reference", "builtin"]), default="auto")
 @click.option("--accel", type=click.Choice(["none", "bvh"]), default="none", help="bvh: sphere hierarchy, same image")
+@click.option("--gpus", type=int, default=1, help="GPUs of this node to render on (re-launches itself under torchrun)")
 @click.argument("input_scene_name", type=str)
 def render(width, height, algorithm, pfm_output, png_output, num_of_rays, max_depth, init_state, init_seq,
-           samples_per_pixel, declare_float, variant, precision, parser, accel, input_scene_name):
+           samples_per_pixel, declare_float, variant, precision, parser, accel, gpus, input_scene_name):
+    import os
+
+    if gpus > 1 and "WORLD_SIZE" not in os.environ:  # one process per GPU: hand the same command line to torchrun
+        import socket
+        import subprocess
+
+        with socket.socket() as sock:
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), "-m", "pytracer_b200", *sys.argv[1:]]
+        sys.exit(subprocess.call(cmd))
     samples_per_side = int(sqrt(samples_per_pixel))
     if samples_per_side ** 2 != samples_per_pixel:
         print(f"Error, the number of samples per pixel ({samples_per_pixel}) must be a perfect square")
@@ -107,8 +120,6 @@ def render(width, height, algorithm, pfm_output, png_output, num_of_rays, max_de
         renderer = PointLightRenderer(world=scene.world, background_color=BLACK, **extra)
 
     comm = None
-    import os
-
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:  # launched under torchrun: one rank per GPU
         from .dist import TorchComm
 

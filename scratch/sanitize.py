@@ -1,0 +1,33 @@
+"""Tiny renders through every kernel, for compute-sanitizer (memcheck / racecheck)."""
+import sys; sys.path.insert(0, '.')
+import numpy as np
+from pytracer_b200 import scenes, _abi, tonemap
+from pytracer_b200.device import DeviceScene
+from pytracer_b200.params import make_params
+from pytracer_b200.pcg import PCG
+
+def run(sc, cam, w, h, **kw):
+    rgb, hit, st = sc.render(make_params(w, h, cam, aa_pcg=PCG(42, 54), pt_pcg=PCG(45, 54), **kw), want_hit=True)
+    assert np.isfinite(rgb).all() and st["overflow"] == 0
+    return rgb
+
+world, cam = scenes.demo_scene()
+sc = DeviceScene(world)
+for spp in (1, 2, 6):   # one-pixel tasks (36 strata), multi-pixel tasks, segmented accumulators
+    run(sc, cam, 48, 27, algorithm="pathtracing", samples_per_side=spp, num_of_rays=4, max_depth=3, variant="warp")
+run(sc, cam, 48, 27, algorithm="pathtracing", samples_per_side=2, num_of_rays=3, max_depth=3, variant="mega")
+run(sc, cam, 48, 27, algorithm="pathtracing", samples_per_side=4, num_of_rays=3, max_depth=2, variant="warp",
+    part_mode=_abi.RT_PART_SPP, part_rank=1, part_count=4)
+rs = scenes.random_spheres_scene(150, 3, 4, 10.0, with_light=True)
+big = DeviceScene(rs.world)
+for accel in ("none", "bvh"):
+    for algo in ("flat", "pointlight"):
+        for prec in ("f32", "f64"):
+            run(big, rs.camera, 40, 24, algorithm=algo, samples_per_side=2, precision=prec, out_f64=(prec == "f64"), accel=accel)
+    for variant in ("warp", "mega"):
+        run(big, rs.camera, 40, 24, algorithm="pathtracing", samples_per_side=2, num_of_rays=3, max_depth=3, variant=variant, accel=accel)
+img = np.random.default_rng(1).random((37, 53, 3), dtype=np.float32) * 4
+tonemap.average_luminosity(img)
+tonemap.tone_map(img, 0.7, None, 1.0)
+tonemap.tone_map(img, 0.7, 0.5, 2.2)
+print("sanitize script done")

@@ -706,3 +706,11 @@ def test_bvh_follows_transform_updates_and_full_size_config5():
     a, ha, sa = sc.render(make_params(384, 216, rs.camera, "pointlight", 2, **kw), want_hit=True)
     b, hb, sb = sc.render(make_params(384, 216, rs.camera, "pointlight", 2, accel="bvh", **kw), want_hit=True)
     assert np.array_equal(ha, hb) and np.array_equal(a, b) and sa["rays_shadow"] == sb["rays_shadow"]
+
+
+def test_every_kernel_at_tiny_sizes():
+    """scratch/sanitize.py: each kernel / accumulator mode / accel / precision once at tiny sizes — finite
+    images, no work-stack overflow (the script is also what one would run under a memory checker)."""
+    import runpy, os
+
+    runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scratch", "sanitize.py"))
