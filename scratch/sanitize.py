@@ -26,6 +26,19 @@ for accel in ("none", "bvh"):
             run(big, rs.camera, 40, 24, algorithm=algo, samples_per_side=2, precision=prec, out_f64=(prec == "f64"), accel=accel)
     for variant in ("warp", "mega"):
         run(big, rs.camera, 40, 24, algorithm="pathtracing", samples_per_side=2, num_of_rays=3, max_depth=3, variant=variant, accel=accel)
+# branching factors and depths at the edges of the work-stack sizing: N = 1 (a chain), deep trees, N larger
+# than a warp, N beyond the multiply-shift division (1024); mega is the yardstick for the image mean
+def lum(rgb):
+    return float(((rgb.max(-1) + rgb.min(-1)) / 2).mean())
+
+for n, depth, rr in ((1, 8, 3), (2, 6, 4), (40, 2, 2), (1100, 1, 3), (3, 0, 3)):
+    for scene, camera, accels in ((sc, cam, ("none",)), (big, rs.camera, ("none", "bvh"))):
+        ref = lum(run(scene, camera, 32, 18, algorithm="pathtracing", samples_per_side=3, num_of_rays=n, max_depth=depth, rr_limit=rr, variant="mega"))
+        for accel in accels:
+            got = lum(run(scene, camera, 32, 18, algorithm="pathtracing", samples_per_side=3, num_of_rays=n, max_depth=depth, rr_limit=rr,
+                          variant="warp", accel=accel))
+            assert abs(got - ref) <= 0.08 * ref + 1e-3, (n, depth, accel, got, ref)
+
 img = np.random.default_rng(1).random((37, 53, 3), dtype=np.float32) * 4
 tonemap.average_luminosity(img)
 tonemap.tone_map(img, 0.7, None, 1.0)
