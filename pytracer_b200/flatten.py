@@ -187,15 +187,27 @@ def flatten_world(world) -> FlatScene:
 
     shapes = list(world.shapes)
     n = len(shapes)
-    kind = np.zeros(n, dtype=np.int32)
-    smat = np.zeros(n, dtype=np.int32)
-    m = np.zeros((n, 12), dtype=np.float64)
-    invm = np.zeros((n, 12), dtype=np.float64)
-    for i, shape in enumerate(shapes):
-        kind[i] = _kind_of(shape, _SHAPES, "shape")
-        smat[i] = add_material(shape.material)
-        m[i] = _rows3x4(shape.transformation.m)
-        invm[i] = _rows3x4(shape.transformation.invm)
+    kind_of_type: Dict[type, int] = {}
+    kinds, smats, ms, invms = [], [], [], []
+    for shape in shapes:  # one pass of attribute reads; the matrices are converted in bulk below
+        t = type(shape)
+        k = kind_of_type.get(t)
+        if k is None:
+            k = kind_of_type[t] = _kind_of(shape, _SHAPES, "shape")
+        kinds.append(k)
+        smats.append(add_material(shape.material))
+        tr = shape.transformation
+        ms.append(tr.m)
+        invms.append(tr.invm)
+    kind = np.array(kinds, dtype=np.int32).reshape(n)
+    smat = np.array(smats, dtype=np.int32).reshape(n)
+
+    def rows(mats) -> np.ndarray:  # n x (4x4 nested lists) -> (n, 12): rows 0..2
+        if not mats:
+            return np.zeros((0, 12), dtype=np.float64)
+        return np.ascontiguousarray(np.array(mats, dtype=np.float64).reshape(n, 4, 4)[:, :3, :].reshape(n, 12))
+
+    m, invm = rows(ms), rows(invms)
 
     mats = (_abi.rt_material * len(material_recs))()
     for dst, (bk, bp, ep, thr) in zip(mats, material_recs):
