@@ -211,6 +211,15 @@ void rt_scene_destroy(rt_scene* scene);
 int rt_scene_update_transforms(rt_scene* scene, int32_t first, int32_t n, const double* m,
                                const double* invm, void* stream);
 
+/* The sphere hierarchy of RT_ACCEL_BVH as rt_render builds it, computed on the HOST (needs no device; used
+ * by the CPU test-suite to check the tree's invariants and the conservativeness of its padded boxes).
+ * m: double[n_spheres][12], Transformation.m rows 0..2 of the spheres.  nodes_out: float[cap_nodes][16]
+ * (per node: lo0.xyz hi0.xyz lo1.xyz hi1.xyz, then four int32 bit patterns ref0 ref1 0 0; a reference
+ * >= 0 is an inner node, < 0 a leaf -(1 + first * 64 + (count - 1)) into prims_out[n_spheres]).
+ * Returns RT_ERR_INVALID if cap_nodes is too small (n_spheres nodes always suffice). */
+int rt_bvh_build_host(const double* m, int32_t n_spheres, float* nodes_out, int32_t cap_nodes,
+                      int32_t* prims_out, int32_t* n_nodes, int32_t* depth);
+
 /* ---- the hot path: ImageTracer.fire_all_rays(renderer) ---- */
 /* Host buffers: out_rgb float[H][W][3] (or double if out_f64), out_hit_index int32[H][W]
  * (optional; shape hit by the LAST sample of each pixel, -1 = miss). Blocking. */

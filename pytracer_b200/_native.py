@@ -27,6 +27,7 @@ _PROTOTYPES = {
     "rt_last_error": (C.c_char_p, []),
     "rt_scene_create": (C.c_int, [C.POINTER(_abi.rt_scene_desc), C.POINTER(_P)]),
     "rt_scene_destroy": (None, [_P]),
+    "rt_bvh_build_host": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rt_scene_update_transforms": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
     "rt_render": (C.c_int, [_P, C.POINTER(_abi.rt_render_params), _P, _P, C.POINTER(_abi.rt_stats)]),
     "rt_render_device": (C.c_int, [_P, C.POINTER(_abi.rt_render_params), _P, _P, _P]),

@@ -407,6 +407,19 @@ static int ensure(void** ptr, size_t* cap, size_t bytes) {
   return RT_OK;
 }
 
+extern "C" int rt_bvh_build_host(const double* m, int32_t n_spheres, float* nodes_out, int32_t cap_nodes, int32_t* prims_out,
+                                 int32_t* n_nodes, int32_t* depth) {
+  if (!m || !nodes_out || !prims_out || !n_nodes || !depth || n_spheres < 0) return fail(RT_ERR_INVALID, "rt_bvh_build_host: bad argument");
+  BvhBuild b = bvh_build(m, n_spheres);
+  if ((int64_t)b.nodes.size() > cap_nodes) return fail(RT_ERR_INVALID, "rt_bvh_build_host: %zu nodes, room for %d", b.nodes.size(), cap_nodes);
+  static_assert(sizeof(BvhHostNode) == 64, "node layout");
+  if (!b.nodes.empty()) memcpy(nodes_out, b.nodes.data(), b.nodes.size() * sizeof(BvhHostNode));
+  if (!b.prims.empty()) memcpy(prims_out, b.prims.data(), b.prims.size() * sizeof(int32_t));
+  *n_nodes = (int32_t)b.nodes.size();
+  *depth = b.max_depth;
+  return RT_OK;
+}
+
 // Builds (host, rt_bvh.h) and uploads the sphere hierarchy of the scene's current transformations.
 static int ensure_bvh(rt_scene* s, cudaStream_t st) {
   if (s->bvh_valid) return RT_OK;

@@ -195,3 +195,112 @@ def test_builtin_scene_reader_matches_the_reference_parse(tmp_path, monkeypatch)
     back = flatten_world(parse_scene_text(rs.to_scene_text()).world).to_npz_dict()
     for key, val in flatten_world(rs.world).to_npz_dict().items():
         assert np.array_equal(val, back[key]), key
+
+
+# ------------------------------------------------------------------ sphere hierarchy, host builder
+def _build_bvh(m):
+    m = np.ascontiguousarray(m, dtype=np.float64).reshape(-1, 12)
+    n = m.shape[0]
+    nodes = np.zeros((max(n, 1), 16), dtype=np.float32)
+    prims = np.zeros(max(n, 1), dtype=np.int32)
+    n_nodes, depth = ctypes.c_int32(0), ctypes.c_int32(0)
+    lib = _native.load()
+    assert lib.rt_bvh_build_host(m.ctypes.data, n, nodes.ctypes.data, nodes.shape[0], prims.ctypes.data,
+                                 ctypes.byref(n_nodes), ctypes.byref(depth)) == 0, lib.rt_last_error()
+    return nodes[: n_nodes.value], prims, depth.value
+
+
+@pytest.mark.parametrize("n_spheres", [1, 2, 5, 64, 1024])
+def test_bvh_builder_invariants_and_conservative_boxes(n_spheres):
+    """The tree rt_render walks with accel = bvh, built on the host: every sphere sits in exactly one leaf
+    of <= 4, every box contains its subtree's boxes, the leaf boxes contain the ellipsoids with the
+    documented padding, and a float64 walk of the tree finds every sphere a random ray really hits."""
+    rs = scenes.random_spheres_scene(n_spheres, 11, 12, 15.0)
+    fs = flatten_world(rs.world)
+    sph = np.flatnonzero(fs.shape_kind == _abi.RT_SHAPE_SPHERE)
+    m = fs.shape_m.reshape(-1, 12)[sph]          # spheres keep their World.shapes order inside the sorted table
+    invm = fs.shape_invm.reshape(-1, 12)[sph]
+    nodes, prims, depth = _build_bvh(m)
+    refs = nodes[:, 12:14].copy().view(np.int32)
+    boxes = nodes[:, :12].astype(np.float64).reshape(-1, 2, 2, 3)  # node, child, lo/hi, xyz
+    assert depth + 2 <= 48 and len(nodes) <= max(n_spheres, 1)
+
+    def leaf(ref):
+        v = -int(ref) - 1
+        return v >> 6, (v & 63) + 1
+
+    seen = np.zeros(n_spheres, dtype=int)
+    centre = m[:, [3, 7, 11]]
+    half = np.sqrt(m[:, [0, 4, 8]] ** 2 + m[:, [1, 5, 9]] ** 2 + m[:, [2, 6, 10]] ** 2)
+
+    def subtree_box(node):  # also checks containment on the way up
+        out = []
+        for c in range(2):
+            lo, hi = boxes[node, c, 0], boxes[node, c, 1]
+            ref = refs[node, c]
+            if ref >= 0:
+                clo, chi = subtree_box(int(ref))
+            else:
+                first, count = leaf(ref)
+                assert count <= 4
+                if n_spheres <= 4 and c == 1:  # the never-hit second child that wraps a one-leaf scene
+                    out.append((lo, hi))
+                    continue
+                idx = prims[first:first + count]
+                seen[idx] += 1
+                clo, chi = (centre[idx] - half[idx]).min(0), (centre[idx] + half[idx]).max(0)
+                assert (lo < clo).all() and (hi > chi).all()  # padded: strictly outside the exact extent
+            assert (lo <= clo).all() and (hi >= chi).all()
+            out.append((lo, hi))
+        return np.minimum(out[0][0], out[1][0]), np.maximum(out[0][1], out[1][1])
+
+    subtree_box(0)
+    assert (seen == 1).all()
+
+    rng = np.random.default_rng(n_spheres)
+    for _ in range(300):
+        o = rng.uniform(-25, 25, 3); o[2] = rng.uniform(0.1, 8)
+        d = rng.normal(size=3)
+        # spheres the ray line really crosses (exact fp64 quadratic in the sphere's frame)
+        po = invm[:, [0, 1, 2, 4, 5, 6, 8, 9, 10]].reshape(-1, 3, 3) @ o + invm[:, [3, 7, 11]]
+        pd = invm[:, [0, 1, 2, 4, 5, 6, 8, 9, 10]].reshape(-1, 3, 3) @ d
+        a, hb, c = (pd * pd).sum(1), (po * pd).sum(1), (po * po).sum(1) - 1
+        disc = hb * hb - a * c
+        t_far = (-hb + np.sqrt(np.maximum(disc, 0))) / a
+        hit = set(np.flatnonzero((disc > 0) & (t_far > 0)).tolist())
+        # spheres a walk of the tree reaches (slab test on the stored boxes, t >= 0)
+        found, stack = set(), [0]
+        inv = 1.0 / np.where(np.abs(d) < 1e-30, 1e-30, d)
+        while stack:
+            node = stack.pop()
+            for ci in range(2):
+                t0, t1 = (boxes[node, ci, 0] - o) * inv, (boxes[node, ci, 1] - o) * inv
+                if np.minimum(t0, t1).max() <= np.maximum(t0, t1).min() and np.maximum(t0, t1).min() >= 0:
+                    ref = refs[node, ci]
+                    if ref >= 0:
+                        stack.append(int(ref))
+                    else:
+                        first, count = leaf(ref)
+                        found.update(prims[first:first + count].tolist())
+        assert hit <= found
+
+
+def test_tonemap_fast_path_error_stays_inside_its_guard_band():
+    """k_tone_map_ldr (csrc/rt_tonemap.cu) keeps an fp32 byte only if 255*y is further than 5e-4 from an
+    integer, claiming the fp32 value is within 1.4e-4 of the fp64 one.  The same arithmetic in numpy
+    float32 (correctly rounded reciprocal instead of MUFU.RCP's one ulp: 255 * 2^-23 = 3e-5 of slack added)
+    over 4 M values spanning 16 decades and several scales."""
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for scale in (1e-3, 0.37, 1.0, 563.0, 1e5):
+        c = (10.0 ** rng.uniform(-8, 8, size=800_000)).astype(np.float32)
+        s32 = np.float32(scale)
+        s255 = np.float32(255.0) * s32
+        x = c * s32
+        a = c * s255
+        r = np.float32(1.0) / (np.float32(1.0) + x)
+        q32 = (a.astype(np.float64) * r.astype(np.float64)).astype(np.float32)  # one rounding, like the device's fma
+        x64 = c.astype(np.float64) * float(np.float64(scale))
+        q64 = 255.0 * (x64 / (1.0 + x64))
+        worst = max(worst, float(np.abs(q32.astype(np.float64) - q64).max()))
+    assert worst + 255 * 2.0 ** -23 < 1.4e-4 < 5.0e-4, worst
