@@ -1,5 +1,9 @@
-"""Tiny renders through every kernel, for compute-sanitizer (memcheck / racecheck)."""
-import sys; sys.path.insert(0, '.')
+"""Tiny renders through every kernel (run by test_every_kernel_at_tiny_sizes; also the script to put
+under a memory / race checker: `compute-sanitizer python tests/kernel_sweep.py`)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from pytracer_b200 import scenes, _abi, tonemap
 from pytracer_b200.device import DeviceScene

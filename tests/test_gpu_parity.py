@@ -709,8 +709,9 @@ def test_bvh_follows_transform_updates_and_full_size_config5():
 
 
 def test_every_kernel_at_tiny_sizes():
-    """scratch/sanitize.py: each kernel / accumulator mode / accel / precision once at tiny sizes — finite
-    images, no work-stack overflow (the script is also what one would run under a memory checker)."""
+    """tests/kernel_sweep.py: each kernel / accumulator mode / accel / precision once at tiny sizes, and the
+    edges of the work-stack sizing (N = 1, deep trees, N > 32, N > 1024) — finite images, no work-stack
+    overflow, warp == mega in the mean (the script is also what one would run under a memory checker)."""
     import runpy, os
 
-    runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scratch", "sanitize.py"))
+    runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), "kernel_sweep.py"))
