@@ -231,6 +231,12 @@ def run_tonemap(args, rank, local_rank, world_size):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6534.5))
+    traffic = None
+    try:
+        if SCALE == 1:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("tonemap")
+    except Exception:
+        pass
     k_lum, k_map = statistics.mean(lum_ms), statistics.mean(map_ms)
     ms = statistics.mean(total_ms)
     line = {
@@ -241,7 +247,7 @@ def run_tonemap(args, rank, local_rank, world_size):
         "e2e": {"value": n / statistics.mean(e2e), "unit": "pixels/s", "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": 3 * n},
         "gpu_launches": 2 * args.steps, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": 15 * n / (k_map * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": 15 * n / (k_map * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_tone_map_ldr (12 B read + 3 B written per pixel)",
+                     "frac": 15 * n / (k_map * 1e-3) / 1e9 / peak, "traffic": traffic, "kernel": "k_tone_map_ldr (12 B read + 3 B written per pixel)",
                      "kernel_ms": k_map, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6534.5 GB/s",
                      "other_kernel": {"kernel": "k_lum_sum (12 B read per pixel)", "kernel_ms": k_lum,
                                       "achieved": 12 * n / (k_lum * 1e-3) / 1e9, "frac": 12 * n / (k_lum * 1e-3) / 1e9 / peak}},
