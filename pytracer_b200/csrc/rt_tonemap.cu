@@ -184,16 +184,54 @@ static __device__ __forceinline__ unsigned int ldr_byte_fast(float c, float scal
 // one word (128 contiguous bytes per warp store); RT_TM_UNROLL independent quads per thread keep
 // enough loads in flight.
 #define RT_TM_UNROLL 4
+// Two channel values per instruction: the arithmetic of ldr_byte_fast on Blackwell's packed fp32 pipe
+// (mul / add / fma .rn.f32x2 — the same IEEE roundings as the scalar form, half the issue slots; at 14
+// scalar instructions per value the kernel kept the issue port 67 % busy and lost to it a fifth of the
+// copy bandwidth).  MUFU.RCP and the three comparisons per value stay scalar.
+typedef unsigned long long tm_f32x2;
+static __device__ __forceinline__ tm_f32x2 tm_pk(float lo, float hi) { tm_f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+static __device__ __forceinline__ void tm_upk(tm_f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+static __device__ __forceinline__ tm_f32x2 tm_mul2(tm_f32x2 a, tm_f32x2 b) { tm_f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+static __device__ __forceinline__ tm_f32x2 tm_add2(tm_f32x2 a, tm_f32x2 b) { tm_f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+static __device__ __forceinline__ tm_f32x2 tm_sub2(tm_f32x2 a, tm_f32x2 b) { tm_f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+static __device__ __forceinline__ tm_f32x2 tm_fma2(tm_f32x2 a, tm_f32x2 b, tm_f32x2 c) { tm_f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+template <bool NORM, bool CLAMP>
+static __device__ __forceinline__ void ldr_pair_fast(float c0, float c1, float scale32, float scale255, unsigned int& b0,
+                                                     unsigned int& b1, bool& unsafe0, bool& unsafe1) {
+  const tm_f32x2 c = tm_pk(c0, c1);
+  const tm_f32x2 x = NORM ? tm_mul2(c, tm_pk(scale32, scale32)) : c;
+  const tm_f32x2 a = tm_mul2(c, NORM ? tm_pk(scale255, scale255) : tm_pk(255.0f, 255.0f));
+  tm_f32x2 h;
+  if (CLAMP) {
+    float d0, d1;
+    tm_upk(tm_add2(x, tm_pk(1.0f, 1.0f)), d0, d1);
+    h = tm_fma2(a, tm_pk(fast_rcp_tm(d0), fast_rcp_tm(d1)), tm_pk(-0.5f, -0.5f));
+  } else {
+    h = tm_add2(a, tm_pk(-0.5f, -0.5f));
+  }
+  const tm_f32x2 magic = tm_pk(RT_TM_MAGIC, RT_TM_MAGIC);
+  const tm_f32x2 tmp = tm_add2(h, magic);
+  const tm_f32x2 d = tm_sub2(h, tm_sub2(tmp, magic));
+  float t0, t1, e0, e1;
+  tm_upk(tmp, t0, t1);
+  tm_upk(d, e0, e1);
+  // safe: frac in (guard, 1 - guard), or the byte is 0 and frac < 1 - guard (q >= 0: it cannot go below 0)
+  unsafe0 = !(e0 < 0.5f - RT_TM_GUARD && (e0 > RT_TM_GUARD - 0.5f || t0 == RT_TM_MAGIC));
+  unsafe1 = !(e1 < 0.5f - RT_TM_GUARD && (e1 > RT_TM_GUARD - 0.5f || t1 == RT_TM_MAGIC));
+  b0 = (unsigned int)__float_as_int(t0) & 0xffu;
+  b1 = (unsigned int)__float_as_int(t1) & 0xffu;
+}
+
 template <bool NORM, bool CLAMP>
 static __device__ __forceinline__ unsigned int ldr_quad(float4 q, const ToneArgs& t, float scale32, float scale255) {
   const float in[4] = {q.x, q.y, q.z, q.w};
-  unsigned int w = 0u, redo = 0u;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    bool unsafe;
-    w |= ldr_byte_fast<NORM, CLAMP>(in[k], scale32, scale255, unsafe) << (8 * k);
-    redo |= (unsafe ? 1u : 0u) << k;
-  }
+  unsigned int b[4];
+  bool u[4];
+  ldr_pair_fast<NORM, CLAMP>(q.x, q.y, scale32, scale255, b[0], b[1], u[0], u[1]);
+  ldr_pair_fast<NORM, CLAMP>(q.z, q.w, scale32, scale255, b[2], b[3], u[2], u[3]);
+  unsigned int w = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+  unsigned int redo = (u[0] ? 1u : 0u) | (u[1] ? 2u : 0u) | (u[2] ? 4u : 0u) | (u[3] ? 8u : 0u);
   if (!(fminf(fminf(q.x, q.y), fminf(q.z, q.w)) >= 0.0f)) redo = 0xfu;  // a negative channel: fp64 for the quad
   while (redo) {  // fp64, the reference's own arithmetic, for the flagged channels
     const int k = __ffs(redo) - 1;
@@ -203,7 +241,6 @@ static __device__ __forceinline__ unsigned int ldr_quad(float4 q, const ToneArgs
   }
   return w;
 }
-
 template <bool NORM, bool CLAMP>
 __global__ void __launch_bounds__(RT_TM_THREADS)
 k_tone_map_ldr(const float* __restrict__ rgb, long long n_pixels, ToneArgs t, unsigned char* __restrict__ out_ldr) {
