@@ -23,8 +23,14 @@ struct PixelMap {
   long long n_pixels;  // pixels this rank traces
   int width, rank, count, rows_mode;
   RT_DEV void locate(long long p, int& col, int& row) const {
-    int lrow = (int)(p / width);
-    col = (int)(p - (long long)lrow * width);
+    int lrow;
+    if (n_pixels < 0x7fffffffLL) {  // (uniform) a 64-bit division is ~100 instructions
+      lrow = (int)((unsigned)p / (unsigned)width);
+      col = (int)((unsigned)p - (unsigned)lrow * (unsigned)width);
+    } else {
+      lrow = (int)(p / width);
+      col = (int)(p - (long long)lrow * width);
+    }
     row = rows_mode ? rank + lrow * count : lrow;
   }
 };
