@@ -42,6 +42,7 @@ struct WarpCfg {
   // registers: background colour in fp32, 1/N, 1/spp, the multiply-shift magic for x / N
   float bg[3], inv_n, inv_spp;
   unsigned n_magic;
+  double inv_w, inv_h, inv_s;  // 1 / width, 1 / height, 1 / samples_per_side (fp64, host-rounded)
   unsigned long long n_samples;  // samples this launch traces (all tasks), added to the counter once
 };
 
@@ -71,6 +72,35 @@ RT_DEV void stage_words(void* sh, const void* g, int bytes) {  // 4-byte granula
   const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
   uint32_t* dst = reinterpret_cast<uint32_t*>(sh);
   for (int i = threadIdx.x; i < bytes / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// Primary ray of the path tracer's warp kernels.  Same formulas as primary_ray<T> (imagetracer.py:48-58,
+// :88-93, camera.py) in fp64, with the five divisions by width / height / S / 0xFFFFFFFF replaced by
+// multiplications with the host-rounded reciprocals: a correctly rounded fp64 division costs ~30
+// instructions and a sample needs six of them.  The fp64 values differ from the reference's by at most an
+// ulp (1e-16), so the fp32 ray they round to is the reference's ray except when a coordinate sits within
+// 1e-16 of an fp32 rounding boundary (~1e-8 of the rays) — immaterial for this renderer, whose parity is
+// statistical; the deterministic renderers, the replay mode and the ray probes keep the divisions.
+RT_DEV Ray<float> primary_ray_mul(const RenderArgs& a, double inv_w, double inv_h, double inv_s, int col, int row, int s, Pcg& aa) {
+  double up = 0.5, vp = 0.5;
+  if (a.S > 0) {
+    const int ir = a.S <= 1024 ? (int)(((float)s + 0.5f) * (float)inv_s) : s / a.S;  // s / S, exact (s < S^2 <= 2^20)
+    const int ic = s - ir * a.S;
+    const double r1 = (double)pcg_random(aa) * (1.0 / 4294967295.0);
+    const double r2 = (double)pcg_random(aa) * (1.0 / 4294967295.0);
+    up = ((double)ic + r1) * inv_s;
+    vp = ((double)ir + r2) * inv_s;
+  }
+  const double u = ((double)col + up) * inv_w;
+  const double v = 1.0 - ((double)row + vp) * inv_h;
+  V3<double> o, d;
+  camera_fire_f64(a.cam, u, v, o, d);
+  Ray<float> r;
+  r.o = cast3<float>(o);
+  r.d = cast3<float>(d);
+  r.tmin = 1.0e-5f;
+  r.tmax = Num<float>::inf();
+  return r;
 }
 
 RT_DEV int own_stratum(const RenderArgs& a, int ls) {
@@ -195,7 +225,7 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
             aa.inc = a.aa_inc;
             if (ACC == ACC_REG) aa.state = (a.S > 0) ? pcg_jump(aa_task, 2ull * (unsigned)s, a.jump) : 0;
             else aa.state = (a.S > 0) ? pcg_jump(a.aa_state, 2ull * k, a.jump) : 0;
-            ray = primary_ray<float>(a, col, row, s, aa);
+            ray = primary_ray_mul(a, cfg.inv_w, cfg.inv_h, cfg.inv_s, col, row, s, aa);
             rng = pcg_seed(a.pt_state, (a.pt_inc >> 1) + k);
             last_of_pixel = (ls == L - 1);
           }
@@ -495,6 +525,9 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   cfg.inv_spp = 1.0f / (float)S2;
   cfg.n_magic = a.num_of_rays <= 1024 ? (65536u + (unsigned)a.num_of_rays - 1u) / (unsigned)a.num_of_rays : 0u;
   cfg.n_samples = (unsigned long long)pm.n_pixels * (unsigned long long)L;
+  cfg.inv_w = 1.0 / (double)a.width;
+  cfg.inv_h = 1.0 / (double)a.height;
+  cfg.inv_s = a.S > 0 ? 1.0 / (double)a.S : 1.0;
 
   void (*kern)(const SceneView<float>, const RenderArgs, const WarpCfg);
 #define RT_PICK(ACCM)                                                                   \

@@ -108,7 +108,7 @@ k_pt_warp_bvh(const __grid_constant__ SceneView<float> sc, const __grid_constant
           Pcg aa;
           aa.inc = a.aa_inc;
           aa.state = (a.S > 0) ? pcg_jump(a.aa_state, 2ull * k, a.jump) : 0;
-          ray = primary_ray<float>(a, col, row, s, aa);
+          ray = primary_ray_mul(a, cfg.inv_w, cfg.inv_h, cfg.inv_s, col, row, s, aa);
           rng_state = pcg_seed(a.pt_state, (a.pt_inc >> 1) + k).state;
           thr = mk3<float>(1.f, 1.f, 1.f);
           depth = 0;
@@ -357,6 +357,9 @@ inline cudaError_t launch_pt_warp_bvh(const SceneView<float>& sc, const RenderAr
   cfg.inv_spp = 1.0f / (float)S2;
   cfg.n_magic = a.num_of_rays <= 1024 ? (65536u + (unsigned)a.num_of_rays - 1u) / (unsigned)a.num_of_rays : 0u;
   cfg.n_samples = (unsigned long long)pm.n_pixels * (unsigned long long)L;
+  cfg.inv_w = 1.0 / (double)a.width;
+  cfg.inv_h = 1.0 / (double)a.height;
+  cfg.inv_s = a.S > 0 ? 1.0 / (double)a.S : 1.0;
   b.refill_at = 20;
   if (const char* env = getenv("RT_BVH_REFILL_AT")) b.refill_at = atoi(env);  // tuning aid
   if (b.refill_at < 0) b.refill_at = 0;
