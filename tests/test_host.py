@@ -304,3 +304,25 @@ def test_tonemap_fast_path_error_stays_inside_its_guard_band():
         q64 = 255.0 * (x64 / (1.0 + x64))
         worst = max(worst, float(np.abs(q32.astype(np.float64) - q64).max()))
     assert worst + 255 * 2.0 ** -23 < 1.4e-4 < 5.0e-4, worst
+
+
+def test_flat_scene_knows_when_only_transformations_changed():
+    """What CudaRenderer.set_world / `animate` use to decide between patching the resident scene
+    (rt_scene_update_transforms) and rebuilding it."""
+    from pytracer_b200.scene import Vec, translation
+
+    a = flatten_world(scenes.demo_scene(clock=10.0)[0])
+    b = flatten_world(scenes.demo_scene(clock=200.0)[0])
+    assert a.differs_only_in_transforms(b) and not np.array_equal(a.shape_m, b.shape_m)
+    w, _ = scenes.demo_scene(clock=10.0)
+    w.shapes[2].material.brdf.pigment.color = Color(0.9, 0.1, 0.1)
+    assert not a.differs_only_in_transforms(flatten_world(w))
+    w, _ = scenes.demo_scene(clock=10.0)
+    w.shapes.pop()
+    assert not a.differs_only_in_transforms(flatten_world(w))
+    w, _ = scenes.demo_scene(clock=10.0)
+    w.point_lights[0].position.x += 1.0
+    assert not a.differs_only_in_transforms(flatten_world(w))
+    w, _ = scenes.demo_scene(clock=10.0)
+    w.shapes[2].transformation = translation(Vec(0.0, 0.0, 2.0))
+    assert a.differs_only_in_transforms(flatten_world(w))
