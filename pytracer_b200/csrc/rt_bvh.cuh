@@ -26,7 +26,7 @@
 
 #include "rt_device.cuh"
 
-#define RT_BVH_STACK 48  // the host builder never goes deeper (rt_bvh.h RT_BVH_MAX_DEPTH)
+#define RT_BVH_STACK 48  // rt_api.cu refuses trees deeper than this minus 2 (rt_bvh.h keeps them far shallower)
 
 struct BvhRay {
   float ox, oy, oz, ix, iy, iz;  // origin, 1 / direction (zeros replaced by a tiny value of the same sign)

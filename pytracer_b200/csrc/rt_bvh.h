@@ -5,6 +5,11 @@
 // box's own extent plus 4e-6 of the extent of the whole set.  The padding is what makes the culling
 // conservative against the fp32 arithmetic of both the slab test and the sphere test (a grazing hit
 // the fp32 quadratic still reports lies within ~1e-5 of the sphere's extent from the true surface).
+// Why that suffices for the slab test too (it runs in fp32 even under the fp64 kernels): rounding the ray
+// origin to fp32 moves it by at most 6e-8 |o|.  For an origin inside ~66 scene extents that is below the
+// absolute pad (4e-6 of the scene extent); for one further out, every box is about |o| away, so the error
+// of the slab parameters is ~1e-7 RELATIVE, which the traversal's own margins (bvh_dn / bvh_up: 1e-6
+// relative on every entry / exit parameter) absorb.
 #pragma once
 #include <algorithm>
 #include <cfloat>
