@@ -35,11 +35,21 @@ RT_DEV void resolve_shade(const SceneView<float>& sc, const RenderArgs& a, Resol
   }
 }
 
-__global__ void __launch_bounds__(RT_RESOLVE_THREADS, 2)
+// BVH (sphere hierarchy instead of the staged sweep) is a template parameter: the walk needs none of the
+// sweep's registers, so its instantiation is held to 80 and three blocks share an SM.
+// Out of line on purpose: the two instantiations below must round the light term identically (inlined,
+// the compiler fuses its products into the caller's additions differently in each, and the linear and the
+// hierarchy image of the same frame would differ in the last bit of every lit pixel).
+static __device__ __noinline__ V3<float> light_term_f32(const SceneView<float>& sc, const Hit<float>& h, V3<float> ray_dir, int l) {
+  return light_term<float>(sc, h, ray_dir, l);
+}
+
+template <bool BVH>
+__global__ void __launch_bounds__(RT_RESOLVE_THREADS, BVH ? 3 : 2)
 k_resolve_f32(const __grid_constant__ SceneView<float> sc, const __grid_constant__ RenderArgs a, const int chunk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n_planes = sc.n_shapes - sc.n_spheres;
-  const bool bvh = sc.accel != 0;  // sphere hierarchy (rt_bvh.cuh): no pair staging, every thread walks the tree
+  constexpr bool bvh = BVH;  // sphere hierarchy (rt_bvh.cuh): no pair staging, every thread walks the tree
   const bool single = bvh || sc.n_pairs <= chunk;
   const bool planes_smem = n_planes <= RT_PLANES_SMEM_MAX;
   const float* planes_g = sc.packed + 24 * (size_t)sc.n_pairs;
@@ -163,8 +173,8 @@ k_resolve_f32(const __grid_constant__ SceneView<float> sc, const __grid_constant
           if (go0) blocked0 = any_candidate_blocks(sc.invm, sc.n_spheres, c0, m0, s0);
           if (go1) blocked1 = any_candidate_blocks(sc.invm, sc.n_spheres, c1, m1, s1);
         }
-        if (need0 && !blocked0) q0.color = q0.color + light_term<float>(sc, q0.h, q0.ray.d, l);
-        if (need1 && !blocked1) q1.color = q1.color + light_term<float>(sc, q1.h, q1.ray.d, l);
+        if (need0 && !blocked0) q0.color = q0.color + light_term_f32(sc, q0.h, q0.ray.d, l);
+        if (need1 && !blocked1) q1.color = q1.color + light_term_f32(sc, q1.h, q1.ray.d, l);
       }
     }
     if (q0.mine) cum = (a.S > 0) ? cum + q0.color : q0.color;
@@ -183,7 +193,8 @@ k_resolve_f32(const __grid_constant__ SceneView<float> sc, const __grid_constant
 inline cudaError_t launch_resolve_f32(const SceneView<float>& sc, const RenderArgs& a, cudaStream_t st, LaunchInfo* info) {
   PixelMap pm = make_pixel_map(a);
   if (pm.n_pixels == 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(k_resolve_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RT_SMEM_SHAPE_BYTES + 17 * 1024);
+  void (*kern)(const SceneView<float>, const RenderArgs, const int) = sc.accel ? k_resolve_f32<true> : k_resolve_f32<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RT_SMEM_SHAPE_BYTES + 17 * 1024);
   if (e != cudaSuccess) return e;
   const int n_planes = sc.n_shapes - sc.n_spheres;
   const size_t planes_bytes = n_planes <= RT_PLANES_SMEM_MAX ? (size_t)n_planes * 48 : 0;
@@ -193,7 +204,7 @@ inline cudaError_t launch_resolve_f32(const SceneView<float>& sc, const RenderAr
   const bool single = sc.n_pairs <= chunk || sc.accel;
   size_t smem = planes_bytes + (size_t)chunk * 96 * (single ? 1 : 2) + 16;  // + two mbarriers
   long long blocks = (pm.n_pixels + RT_RESOLVE_THREADS - 1) / RT_RESOLVE_THREADS;
-  k_resolve_f32<<<(unsigned)blocks, RT_RESOLVE_THREADS, smem, st>>>(sc, a, chunk);
+  kern<<<(unsigned)blocks, RT_RESOLVE_THREADS, smem, st>>>(sc, a, chunk);
   if (info) { info->n_launches += 1; info->variant = 0; }
   return cudaGetLastError();
 }
