@@ -13,6 +13,9 @@
 #include "rt_bvh.cuh"
 
 #define RT_RESOLVE_THREADS 256
+#ifndef RT_RESOLVE_BVH_MINB
+#define RT_RESOLVE_BVH_MINB 3
+#endif
 #define RT_MEGA_THREADS 128
 #define RT_SMEM_SHAPE_BYTES (48 * 1024)
 
@@ -134,8 +137,8 @@ RT_DEV V3<T> light_term(const SceneView<T>& sc, const Hit<T>& h, V3<T> ray_dir, 
 // `chunk` = shapes (fp64) or sphere PAIRS (fp32) staged per sweep step; everything in one chunk when
 // it fits.  fp32 keeps the plane records in a small resident block and sweeps packed sphere pairs;
 // crossed spheres are collected over all chunks and resolved once from global memory.
-template <typename T>
-__global__ void __launch_bounds__(RT_RESOLVE_THREADS)
+template <typename T, bool BVH>
+__global__ void __launch_bounds__(RT_RESOLVE_THREADS, BVH ? RT_RESOLVE_BVH_MINB : 2)
 k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ RenderArgs a, const int chunk) {
   constexpr bool F32 = sizeof(T) == 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -158,7 +161,7 @@ k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
   const long long pix = (long long)row * a.width + col;
   const int S2 = a.S > 0 ? a.S * a.S : 1;
 
-  const bool bvh = sc.accel != 0;  // hierarchy traversal: nothing is staged, every thread walks the tree
+  constexpr bool bvh = BVH;  // hierarchy traversal: nothing is staged, every thread walks the tree
   if (bvh) {
   } else if (F32) {
     if (planes_smem) stage_bytes(sh_planes, planes_g, (size_t)n_planes * 48);
@@ -292,7 +295,8 @@ cudaError_t launch_resolve_generic(const SceneView<T>& sc, const RenderArgs& a, 
   if (pm.n_pixels == 0) return cudaSuccess;
   constexpr bool F32 = sizeof(T) == 4;
   // everything in one chunk while it fits 96 KB of shared memory, else 48 KB chunks
-  cudaError_t e = cudaFuncSetAttribute(k_resolve<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RT_SMEM_SHAPE_BYTES + 16 * 1024);
+  void (*kern)(const SceneView<T>, const RenderArgs, const int) = sc.accel ? k_resolve<T, true> : k_resolve<T, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RT_SMEM_SHAPE_BYTES + 16 * 1024);
   if (e != cudaSuccess) return e;
   const int n_planes = sc.n_shapes - sc.n_spheres;
   const size_t unit = F32 ? 96 : 12 * sizeof(T);
@@ -301,7 +305,7 @@ cudaError_t launch_resolve_generic(const SceneView<T>& sc, const RenderArgs& a, 
   int chunk = (size_t)n_units * unit <= 2 * RT_SMEM_SHAPE_BYTES ? (n_units > 0 ? n_units : 1) : (int)(RT_SMEM_SHAPE_BYTES / unit);
   size_t smem = sc.accel ? 16 : planes_bytes + (size_t)chunk * unit;
   long long blocks = (pm.n_pixels + RT_RESOLVE_THREADS - 1) / RT_RESOLVE_THREADS;
-  k_resolve<T><<<(unsigned)blocks, RT_RESOLVE_THREADS, smem, st>>>(sc, a, chunk);
+  kern<<<(unsigned)blocks, RT_RESOLVE_THREADS, smem, st>>>(sc, a, chunk);
   if (info) { info->n_launches += 1; info->variant = 0; }
   return cudaGetLastError();
 }
