@@ -38,9 +38,13 @@ enum { RT_CAMERA_ORTHOGONAL = 0, RT_CAMERA_PERSPECTIVE = 1 };
 /* main.py:73 RENDERERS, in the reference's order */
 enum { RT_ALGO_ONOFF = 0, RT_ALGO_FLAT = 1, RT_ALGO_PATHTRACING = 2, RT_ALGO_POINTLIGHT = 3 };
 
-/* Arithmetic type of the traced path. AUTO = F64 for the deterministic renderers (their
- * hit index must be bit-exact against the fp64 reference), F32 for path tracing. */
-enum { RT_PRECISION_AUTO = 0, RT_PRECISION_F32 = 1, RT_PRECISION_F64 = 2 };
+/* Arithmetic type of the traced path.  F32: fp32 throughout (path tracing's production arithmetic).
+ * F64: fp64 without multiply-add fusion, the reference's own decisions (hit index bit-exact).
+ * HYBRID (deterministic renderers, perspective camera, RT_ACCEL_NONE): an fp32 sweep that provably
+ * never drops a sphere the reference hits, then the F64 code on the few spheres that pass — the F64
+ * image bit for bit, at the speed of the fp32 sweep.
+ * AUTO = F32 for path tracing; HYBRID for the deterministic renderers where it applies, else F64. */
+enum { RT_PRECISION_AUTO = 0, RT_PRECISION_F32 = 1, RT_PRECISION_F64 = 2, RT_PRECISION_HYBRID = 3 };
 
 /* Path-tracer kernel. MEGA = one thread per pixel-sample walking the recursion of
  * render.py:99-139 depth-first in the reference's own order; WARP = warp-cooperative

@@ -11,6 +11,6 @@ from .scene import (  # noqa: F401
     create_onb_from_z, rotation_x, rotation_y, rotation_z, scaling, translation,
 )
 from .pcg import PCG  # noqa: F401
-from .hdrimage import HdrImage, read_pfm_image  # noqa: F401
+from .hdrimage import Endianness, HdrImage, read_pfm_image  # noqa: F401
 
 __version__ = "0.1.0"

@@ -11,8 +11,8 @@ RT_PIGMENT_UNIFORM, RT_PIGMENT_CHECKERED, RT_PIGMENT_IMAGE = 0, 1, 2
 RT_CAMERA_ORTHOGONAL, RT_CAMERA_PERSPECTIVE = 0, 1
 RT_ALGO_ONOFF, RT_ALGO_FLAT, RT_ALGO_PATHTRACING, RT_ALGO_POINTLIGHT = 0, 1, 2, 3
 ALGORITHMS = {"onoff": 0, "flat": 1, "pathtracing": 2, "pointlight": 3}
-RT_PRECISION_AUTO, RT_PRECISION_F32, RT_PRECISION_F64 = 0, 1, 2
-PRECISIONS = {"auto": 0, "f32": 1, "f64": 2}
+RT_PRECISION_AUTO, RT_PRECISION_F32, RT_PRECISION_F64, RT_PRECISION_HYBRID = 0, 1, 2, 3
+PRECISIONS = {"auto": 0, "f32": 1, "f64": 2, "hybrid": 3}
 RT_VARIANT_AUTO, RT_VARIANT_MEGA, RT_VARIANT_WARP = 0, 1, 2
 VARIANTS = {"auto": 0, "mega": 1, "warp": 2}
 RT_RNG_STREAMS, RT_RNG_REPLAY = 0, 1

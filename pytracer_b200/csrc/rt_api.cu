@@ -59,6 +59,8 @@ struct Workspace {
   size_t ldr_cap = 0;
   void* hdr_out = nullptr;
   size_t hdr_out_cap = 0;
+  void* co = nullptr;  // per-(origin, sphere) gate records of the hybrid resolve kernel
+  size_t co_cap = 0;
 };
 
 struct rt_scene {
@@ -398,6 +400,15 @@ static int fill_args(const rt_scene* s, const rt_render_params* p, RenderArgs* a
   return RT_OK;
 }
 
+// samples (Renderer.__call__ invocations) this rank's share of the image holds
+static long long make_pixel_count(const RenderArgs& a) {
+  long long S2 = a.S > 0 ? (long long)a.S * a.S : 1;
+  long long rows = a.height, strata = S2;
+  if (a.part_mode == RT_PART_ROWS && a.part_count > 1) rows = (a.height - a.part_rank + a.part_count - 1) / a.part_count;
+  if (a.part_mode == RT_PART_SPP && a.part_count > 1) strata = a.part_rank < S2 ? (S2 - a.part_rank + a.part_count - 1) / a.part_count : 0;
+  return std::max(rows, 0ll) * a.width * strata;
+}
+
 static int ensure(void** ptr, size_t* cap, size_t bytes) {
   if (*cap >= bytes && *ptr) return RT_OK;
   if (*ptr) cudaFree(*ptr);
@@ -453,13 +464,20 @@ extern "C" int rt_render_device(rt_scene* s, const rt_render_params* p, void* d_
   a.out_rgb = d_out_rgb;
   a.out_hit = d_out_hit;
   const bool pt = p->algorithm == RT_ALGO_PATHTRACING;
-  int precision = p->precision == RT_PRECISION_AUTO ? (pt ? RT_PRECISION_F32 : RT_PRECISION_F64) : p->precision;
-  if (precision != RT_PRECISION_F32 && precision != RT_PRECISION_F64) return fail(RT_ERR_INVALID, "precision %d", p->precision);
+  // the hybrid path needs a common ray origin (perspective camera) and sweeps every sphere (no hierarchy)
+  const bool hybrid_ok = !pt && p->camera.kind == RT_CAMERA_PERSPECTIVE && p->accel == RT_ACCEL_NONE;
+  int precision = p->precision;
+  if (precision == RT_PRECISION_AUTO) precision = pt ? RT_PRECISION_F32 : (hybrid_ok ? RT_PRECISION_HYBRID : RT_PRECISION_F64);
+  if (precision == RT_PRECISION_HYBRID && !hybrid_ok)
+    return fail(RT_ERR_INVALID, "RT_PRECISION_HYBRID needs a deterministic renderer, a perspective camera and RT_ACCEL_NONE");
+  if (precision != RT_PRECISION_F32 && precision != RT_PRECISION_F64 && precision != RT_PRECISION_HYBRID)
+    return fail(RT_ERR_INVALID, "precision %d", p->precision);
   int variant = p->variant;
+  const bool auto_variant = variant == RT_VARIANT_AUTO;
   if (pt) {
-    if (p->num_of_rays < 1 || p->max_depth < 0) return fail(RT_ERR_INVALID, "num_of_rays %d, max_depth %d", p->num_of_rays, p->max_depth);
+    if (p->num_of_rays < 1) return fail(RT_ERR_INVALID, "num_of_rays %d", p->num_of_rays);
     if (variant == RT_VARIANT_AUTO)
-      variant = (p->rng_mode == RT_RNG_REPLAY || precision == RT_PRECISION_F64 || p->max_depth < 0) ? RT_VARIANT_MEGA : RT_VARIANT_WARP;
+      variant = (p->rng_mode == RT_RNG_REPLAY || precision == RT_PRECISION_F64) ? RT_VARIANT_MEGA : RT_VARIANT_WARP;
     if (variant == RT_VARIANT_WARP && (p->rng_mode == RT_RNG_REPLAY || precision == RT_PRECISION_F64))
       return fail(RT_ERR_INVALID, "the warp variant is fp32 with per-sample streams; replay / fp64 need the mega variant");
     if (p->rng_mode == RT_RNG_REPLAY) {
@@ -492,7 +510,19 @@ extern "C" int rt_render_device(rt_scene* s, const rt_render_params* p, void* d_
   CU(cudaEventRecord(s->ws->ev0, st));
   cudaError_t e = cudaSuccess;
   const char* why = nullptr;
-  if (!pt) {
+  if (pt && p->max_depth < 0) {
+    // render.py:100-101: every primary ray already has depth 0 > max_depth, so each sample is BLACK and
+    // no ray is traced — the image is zero whatever the scene
+    long long n = (long long)make_pixel_count(a);
+    unsigned long long samples = (unsigned long long)n;
+    e = cudaMemsetAsync(d_out_rgb, 0, px * 3 * (a.out_f64 ? sizeof(double) : sizeof(float)), st);
+    if (e == cudaSuccess && d_out_hit) e = cudaMemsetAsync(d_out_hit, 0xff, px * sizeof(int32_t), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->ws->counters + CNT_SAMPLES, &samples, sizeof(samples), cudaMemcpyHostToDevice, st);
+    s->last_info.variant = variant;
+  } else if (!pt && precision == RT_PRECISION_HYBRID) {
+    if ((rc = ensure(&s->ws->co, &s->ws->co_cap, resolve_hybrid_table_bytes(s->n_spheres, s->n_lights))) != RT_OK) return rc;
+    e = launch_resolve_hybrid(v64, a, (float*)s->ws->co, st, &s->last_info);
+  } else if (!pt) {
     e = precision == RT_PRECISION_F64 ? launch_resolve<double>(v64, a, st, &s->last_info)
                                       : launch_resolve<float>(v32, a, st, &s->last_info);
   } else if (variant == RT_VARIANT_MEGA) {
@@ -501,6 +531,14 @@ extern "C" int rt_render_device(rt_scene* s, const rt_render_params* p, void* d_
     if (e == cudaErrorInvalidValue) why = "max_depth > 64 with num_of_rays > 1 is not supported by the mega variant";
   } else {
     e = launch_pt_warp(v32, a, st, s->sm_count, &s->last_info, &why, s->bvh_n_nodes, s->bvh_n_prims, s->bvh_depth);
+    if (e == cudaErrorInvalidValue && why && auto_variant) {
+      // a configuration the wavefront kernel refuses (work stack deeper than shared memory holds):
+      // AUTO falls back to the depth-first megakernel instead of failing
+      cudaGetLastError();
+      why = nullptr;
+      e = launch_pt_mega<float>(v32, a, st, &s->last_info);
+      if (e == cudaErrorInvalidValue) why = "max_depth > 64 with num_of_rays > 1 is supported by neither path-tracer kernel";
+    }
   }
   if (e != cudaSuccess) return fail(why ? RT_ERR_INVALID : RT_ERR_CUDA, "render launch: %s", why ? why : cudaGetErrorString(e));
   CU(cudaEventRecord(s->ws->ev1, st));
@@ -582,7 +620,7 @@ static int run_probe(rt_scene* s, int precision, const rt_render_params* p, int 
   }
   int rc = fill_args(s, p, &a);
   if (rc != RT_OK) return rc;
-  if (precision == RT_PRECISION_AUTO) precision = RT_PRECISION_F64;
+  if (precision == RT_PRECISION_AUTO || precision == RT_PRECISION_HYBRID) precision = RT_PRECISION_F64;  // single items: plain fp64
   auto align = [](size_t x) { return (x + 255) / 256 * 256; };
   size_t off_in = 0, off_depth = align(in_bytes), off_pcg = off_depth + align(depth ? n * sizeof(int32_t) : 0);
   size_t off_out = off_pcg + 256, total = off_out + align(out_bytes);
@@ -864,7 +902,14 @@ extern "C" int rt_host_register(void* ptr, uint64_t bytes) {
   if (!ptr || bytes == 0) return fail(RT_ERR_INVALID, "rt_host_register: bad argument");
   if (rt_device_count() <= 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
   cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
-  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return RT_OK; }
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    // fine only if it is this very range that is registered (same caller pinning twice); an overlapping
+    // older registration of a recycled address would leave part of the range pageable
+    cudaGetLastError();
+    cudaError_t u = cudaHostUnregister(ptr);
+    if (u == cudaSuccess) e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    else cudaGetLastError();
+  }
   if (e != cudaSuccess) return fail(RT_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
   return RT_OK;
 }

@@ -58,18 +58,9 @@ RT_DEV bool bvh_box_hit(float tn, float tf, float tmin, float limit) {
 }
 
 template <typename T> RT_DEV T bvh_sphere_t(const SceneView<T>& sc, int i, const Ray<T>& r, int origin);
-// fp32: exactly what the linear path does with a sphere — the sweep keeps it iff delta/4 > 0
-// (sphere_qdelta rounds like the packed sweep), then resolve_candidates calls sphere_t_at
+// fp32: the function the linear path resolves its candidates with (sphere_t_at, rt_device.cuh)
 template <> RT_DEV float bvh_sphere_t<float>(const SceneView<float>& sc, int i, const Ray<float>& r, int origin) {
-  const float* im = sc.invm + 12 * (size_t)i;
-  float a, hb;
-  const float qd = sphere_qdelta(im, r, a, hb);
-  if (!(qd > 0.0f)) return Num<float>::inf();
-  if (i == origin) {
-    const float t = -2.0f * hb * fast_rcp(a);
-    return (t > r.tmin && t < r.tmax) ? t : Num<float>::inf();
-  }
-  return sphere_root(a, hb, qd, r.tmin, r.tmax);
+  return sphere_t_at(sc.invm + 12 * (size_t)i, r, i == origin);
 }
 template <> RT_DEV double bvh_sphere_t<double>(const SceneView<double>& sc, int i, const Ray<double>& r, int) {
   return sphere_t<double>(sc.invm + 12 * (size_t)i, r);

@@ -168,7 +168,16 @@ RT_DEV bool scan_any(const T* __restrict__ xf, int begin, int end, int n_spheres
 // Spheres are tested four at a time; the few whose line is crossed (delta > 0) go to a per-lane
 // candidate list and only those get the sqrt / reciprocal / range tests after the sweep — so the
 // sweep itself has one (rarely taken) branch per four spheres.
-RT_DEV float sphere_qdelta(const float* __restrict__ im, const Ray<float>& r, float& a, float& hb) {
+//
+// Does the ray's line cross the sphere, and where: evaluated from the point of the line closest to the
+// centre, q = o' - (o'.d' / a) d', instead of from the discriminant.  The line crosses iff |q|^2 < 1 and
+// the roots are t = tm -+ half with tm = -(o'.d') / a, half = sqrt((1 - |q|^2) / a) — the same numbers as
+// (-b -+ sqrt(delta)) / 2a (shapes.py:103-121), but delta/4 = (o'.d')^2 - a (|o'|^2 - 1) subtracts two
+// terms of size a |o'|^2 to find something of size a: for a ray that starts 10^3 radii away its fp32 value
+// is rounding noise (phantom hits on spheres the ray passes at a distance), while |q|^2 is formed from a
+// vector of the size of the answer.  The sweep keeps the cheap discriminant as its gate; every decision
+// about a sphere (closest hit, shadow test, hierarchy leaf) comes from here.
+RT_DEV bool sphere_cross(const float* __restrict__ im, const Ray<float>& r, float& tm, float& half) {
   const float4 r0 = reinterpret_cast<const float4*>(im)[0];
   const float4 r1 = reinterpret_cast<const float4*>(im)[1];
   const float4 r2 = reinterpret_cast<const float4*>(im)[2];
@@ -178,19 +187,15 @@ RT_DEV float sphere_qdelta(const float* __restrict__ im, const Ray<float>& r, fl
   const float dx = fmaf(r0.x, r.d.x, fmaf(r0.y, r.d.y, r0.z * r.d.z));
   const float dy = fmaf(r1.x, r.d.x, fmaf(r1.y, r.d.y, r1.z * r.d.z));
   const float dz = fmaf(r2.x, r.d.x, fmaf(r2.y, r.d.y, r2.z * r.d.z));
-  a = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-  hb = fmaf(px, dx, fmaf(py, dy, pz * dz));
-  const float c = fmaf(px, px, fmaf(py, py, fmaf(pz, pz, -1.0f)));
-  return fmaf(hb, hb, -(a * c));  // same rounding as the packed sweep (ptxas fuses its sub into FFMA2 with -ac)
-}
-
-// roots of the crossed sphere: t = (-b/2 -+ sqrt(delta/4)) / a, first one inside (tmin, tmax)
-RT_DEV float sphere_root(float a, float hb, float qd, float tmin, float tmax) {
-  const float sd = fast_sqrt(qd), inv = fast_rcp(a);
-  const float t1 = (-hb - sd) * inv, t2 = (-hb + sd) * inv;
-  if (t1 > tmin && t1 < tmax) return t1;
-  if (t2 > tmin && t2 < tmax) return t2;
-  return Num<float>::inf();
+  const float a = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+  const float hb = fmaf(px, dx, fmaf(py, dy, pz * dz));
+  const float inv = fast_rcp(a);
+  const float s = hb * inv;
+  const float qx = fmaf(-s, dx, px), qy = fmaf(-s, dy, py), qz = fmaf(-s, dz, pz);
+  const float w = (1.0f - fmaf(qx, qx, fmaf(qy, qy, qz * qz))) * inv;
+  tm = -s;
+  half = fast_sqrt(fmaxf(w, 0.0f));
+  return w > 0.0f;  // false for a = 0 too (s is NaN): the reference's delta = b^2 = 0 is a miss as well
 }
 
 #define RT_CAND_CAP 16
@@ -371,13 +376,17 @@ RT_DEV void sweep_pairs_split(const float4* __restrict__ pairs, int n_pairs, con
 // origin sphere the exact second root -2(b/2)/a is used instead: what the reference computes, without
 // the cancellation.
 RT_DEV float sphere_t_at(const float* __restrict__ im, const Ray<float>& r, bool is_origin) {
-  float a, hb;
-  const float qd = sphere_qdelta(im, r, a, hb);
+  float tm, half;
+  const bool cross = sphere_cross(im, r, tm, half);
   if (is_origin) {
-    const float t = -2.0f * hb * fast_rcp(a);
+    const float t = 2.0f * tm;  // -2 (b/2) / a
     return (t > r.tmin && t < r.tmax) ? t : Num<float>::inf();
   }
-  return qd > 0.0f ? sphere_root(a, hb, qd, r.tmin, r.tmax) : Num<float>::inf();
+  if (!cross) return Num<float>::inf();
+  const float t1 = tm - half, t2 = tm + half;  // the first root inside (tmin, tmax), shapes.py:112-119
+  if (t1 > r.tmin && t1 < r.tmax) return t1;
+  if (t2 > r.tmin && t2 < r.tmax) return t2;
+  return Num<float>::inf();
 }
 
 RT_DEV void resolve_candidates(const float* __restrict__ invm, int n_spheres, const int* cand, int nc,
@@ -397,11 +406,9 @@ RT_DEV void resolve_candidates(const float* __restrict__ invm, int n_spheres, co
 }
 
 RT_DEV bool sphere_blocks(const float* __restrict__ im, const Ray<float>& r) {
-  float a, hb;
-  const float qd = sphere_qdelta(im, r, a, hb);
-  if (!(qd > 0.0f)) return false;
-  const float sd = fast_sqrt(qd), inv = fast_rcp(a);
-  const float t1 = (-hb - sd) * inv, t2 = (-hb + sd) * inv;
+  float tm, half;
+  if (!sphere_cross(im, r, tm, half)) return false;
+  const float t1 = tm - half, t2 = tm + half;
   return (r.tmin < t1 && t1 < r.tmax) || (r.tmin < t2 && t2 < r.tmax);
 }
 
@@ -483,13 +490,11 @@ RT_DEV void closest_all_warp(const SceneView<float>& sc, const ScanSrc<float>& s
 // tests are written without branches: with 32 different rays per warp some lane crosses every shape
 // anyway, so a branch only adds its own overhead.  Same decisions as sphere_t_at / plane_t.
 RT_DEV float sphere_t_few(const float* __restrict__ im, const Ray<float>& r, bool is_origin) {
-  float a, hb;
-  const float qd = sphere_qdelta(im, r, a, hb);
-  const float sd = fast_sqrt(fmaxf(qd, 0.0f)), inv = fast_rcp(a);
-  const float t1 = (-hb - sd) * inv, t2 = (-hb + sd) * inv;
+  float tm, half;
+  bool ok = sphere_cross(im, r, tm, half);
+  const float t1 = tm - half, t2 = tm + half;
   float t = (t1 > r.tmin && t1 < r.tmax) ? t1 : t2;  // the first root inside (tmin, tmax), shapes.py:112-119
-  bool ok = qd > 0.0f;
-  if (is_origin) { t = -2.0f * hb * inv; ok = true; }  // see sphere_t_at
+  if (is_origin) { t = 2.0f * tm; ok = true; }  // see sphere_t_at
   return (ok && t > r.tmin && t < r.tmax) ? t : Num<float>::inf();
 }
 RT_DEV float plane_t_few(const float* __restrict__ im, const Ray<float>& r, bool is_origin) {

@@ -28,6 +28,10 @@ struct LaunchInfo {
 
 // Explicitly instantiated for float in rt_kernels_f32.cu and for double in rt_kernels_f64.cu.
 template <typename T> cudaError_t launch_resolve(const SceneView<T>& sc, const RenderArgs& a, cudaStream_t st, LaunchInfo* info);
+// rt_kernels_f64.cu: fp32 conservative gate + the reference's fp64 decisions (rt_resolve_hybrid.cuh); `co` is
+// device scratch of resolve_hybrid_table_bytes() bytes, perspective cameras only
+size_t resolve_hybrid_table_bytes(int n_spheres, int n_lights);
+cudaError_t launch_resolve_hybrid(const SceneView<double>& sc, const RenderArgs& a, float* co, cudaStream_t st, LaunchInfo* info);
 template <typename T> cudaError_t launch_pt_mega(const SceneView<T>& sc, const RenderArgs& a, cudaStream_t st, LaunchInfo* info);
 // fp32 only (rt_kernels_f32.cu): the warp-cooperative wavefront path tracer
 // (n_nodes / n_prims / tree_depth describe the sphere hierarchy and are read only when sc.accel != 0)

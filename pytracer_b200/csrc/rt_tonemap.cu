@@ -176,6 +176,9 @@ static __device__ __forceinline__ unsigned int ldr_byte_fast(float c, float scal
   const float d = h - (tmp - RT_TM_MAGIC);
   // safe: frac in (guard, 1 - guard), or the byte is 0 and frac < 1 - guard (q >= 0: it cannot go below 0)
   unsafe = !(d < 0.5f - RT_TM_GUARD && (d > RT_TM_GUARD - 0.5f || tmp == RT_TM_MAGIC));
+  // without clamp_image a channel can exceed 1: the low mantissa byte would wrap modulo 256 where the
+  // reference saturates (PIL clips), so anything from 255.5 up goes to the exact path (which returns 255)
+  if (!CLAMP) unsafe = unsafe || !(h < 255.0f);
   return (unsigned int)__float_as_int(tmp) & 0xffu;
 }
 
@@ -219,6 +222,12 @@ static __device__ __forceinline__ void ldr_pair_fast(float c0, float c1, float s
   // safe: frac in (guard, 1 - guard), or the byte is 0 and frac < 1 - guard (q >= 0: it cannot go below 0)
   unsafe0 = !(e0 < 0.5f - RT_TM_GUARD && (e0 > RT_TM_GUARD - 0.5f || t0 == RT_TM_MAGIC));
   unsafe1 = !(e1 < 0.5f - RT_TM_GUARD && (e1 > RT_TM_GUARD - 0.5f || t1 == RT_TM_MAGIC));
+  if (!CLAMP) {  // values past 255.5 would wrap modulo 256 in the mantissa trick: exact path (saturates like PIL)
+    float h0, h1;
+    tm_upk(h, h0, h1);
+    unsafe0 = unsafe0 || !(h0 < 255.0f);
+    unsafe1 = unsafe1 || !(h1 < 255.0f);
+  }
   b0 = (unsigned int)__float_as_int(t0) & 0xffu;
   b1 = (unsigned int)__float_as_int(t1) & 0xffu;
 }

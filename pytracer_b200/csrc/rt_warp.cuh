@@ -464,7 +464,6 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
     L = a.part_rank < S2 ? (S2 - a.part_rank + a.part_count - 1) / a.part_count : 0;
   if (pm.n_pixels == 0 || L == 0) return cudaSuccess;
   if (a.num_of_rays < 1) { *why_not = "num_of_rays must be >= 1"; return cudaErrorInvalidValue; }
-  if (a.max_depth < 0) { *why_not = "max_depth < 0 (an all-black image) is left to the mega variant"; return cudaErrorInvalidValue; }
   if (a.max_depth >= 1023) { *why_not = "max_depth >= 1023 is not supported by the warp variant (use mega)"; return cudaErrorInvalidValue; }
   WarpCfg cfg;
   cfg.per_pixel = L;
@@ -477,7 +476,9 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
   // (multi-pixel tasks, L < 32: 32 samples per task keep the accumulator columns small enough for three
   // resident blocks per SM — measured on demo.txt split over 8 GPUs: 50.9 vs 41.4 Grays/s per GPU)
   int want = 32;
-  if (const char* env = getenv("RT_WARP_WANT")) want = atoi(env);  // tuning aid: samples per task
+#ifdef RT_TUNING  // tuning builds only (-DRT_TUNING): samples per multi-pixel task, clamped to what the kernel supports
+  if (const char* env = getenv("RT_WARP_WANT")) want = std::min(std::max(atoi(env), 1), 256);
+#endif
   if (L >= 32) cfg.group = 1;
   else if (L >= 4) cfg.group = (want + L - 1) / L < RT_ACC_LANES_MAX_GROUP ? (want + L - 1) / L : RT_ACC_LANES_MAX_GROUP;
   else cfg.group = 32 / L;
@@ -511,7 +512,9 @@ inline cudaError_t launch_pt_warp_impl(const SceneView<float>& sc, const RenderA
     const size_t blocks_seg = sm_bytes / (footprint(ACC_SEG, warps, pw_s) + 1024);
     const size_t by_threads = 2048 / (warps * 32), by_regs = small ? RT_SMALL_MINB : 2;
     if (std::min(std::min(blocks_seg, by_threads), by_regs) > std::min(std::min(blocks_lanes, by_threads), by_regs)) acc_mode = ACC_SEG;
-    if (const char* env = getenv("RT_WARP_ACC")) acc_mode = atoi(env);  // tuning aid
+#ifdef RT_TUNING
+    if (const char* env = getenv("RT_WARP_ACC")) { const int m = atoi(env); if (m == ACC_LANES || m == ACC_SEG) acc_mode = m; }
+#endif
   }
   for (;; warps >>= 1) {
     smem = footprint(acc_mode, warps, per_warp);

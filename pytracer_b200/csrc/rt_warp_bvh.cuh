@@ -361,11 +361,15 @@ inline cudaError_t launch_pt_warp_bvh(const SceneView<float>& sc, const RenderAr
   cfg.inv_h = 1.0 / (double)a.height;
   cfg.inv_s = a.S > 0 ? 1.0 / (double)a.S : 1.0;
   b.refill_at = 20;
-  if (const char* env = getenv("RT_BVH_REFILL_AT")) b.refill_at = atoi(env);  // tuning aid
+#ifdef RT_TUNING
+  if (const char* env = getenv("RT_BVH_REFILL_AT")) b.refill_at = atoi(env);
+#endif
   if (b.refill_at < 0) b.refill_at = 0;
   if (b.refill_at > 31) b.refill_at = 31;
   b.inner_min = 8;
+#ifdef RT_TUNING
   if (const char* env = getenv("RT_BVH_INNER_MIN")) b.inner_min = atoi(env);
+#endif
   if (b.inner_min < 0) b.inner_min = 0;
   if (b.inner_min > 31) b.inner_min = 31;
 

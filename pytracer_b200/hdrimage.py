@@ -13,6 +13,7 @@ header ``PF\\n<w> <h>\\n<-1.0|1.0>\\n`` then rows bottom-to-top of fp32 RGB.
 """
 from __future__ import annotations
 
+import enum
 from typing import Optional
 
 import numpy as np
@@ -22,6 +23,24 @@ from .scene import Color
 
 class InvalidPfmFileFormat(Exception):
     pass
+
+
+class Endianness(enum.Enum):
+    """hdrimages.py:31-35"""
+
+    LITTLE_ENDIAN = 1
+    BIG_ENDIAN = 2
+
+
+def _is_little_endian(endianness) -> bool:
+    """Accepts this module's enum, the reference's ``pytracer.hdrimages.Endianness`` (duck-typed on
+    ``.name``) or a plain bool (True = little endian)."""
+    if isinstance(endianness, bool):
+        return endianness
+    name = getattr(endianness, "name", None)
+    if name in ("LITTLE_ENDIAN", "BIG_ENDIAN"):
+        return name == "LITTLE_ENDIAN"
+    raise TypeError(f"endianness must be an Endianness member or a bool, not {endianness!r}")
 
 
 class PixelView:
@@ -69,6 +88,7 @@ class HdrImage:
         Returns False when the buffer cannot be pinned (no device, tiny image): copies still work."""
         if getattr(self, "_pinned_ptr", None) == self._rgb.ctypes.data:
             return True
+        self.unpin()  # the buffer was replaced since the last pin
         if self._rgb.nbytes < (1 << 16):
             return False
         try:
@@ -82,9 +102,11 @@ class HdrImage:
         self._pinned_ptr = self._rgb.ctypes.data
         return True
 
-    def __del__(self):
+    def unpin(self) -> None:
+        """Undo :meth:`pin` (called before the pixel buffer is replaced or freed)."""
         ptr = getattr(self, "_pinned_ptr", None)
         if ptr:
+            self._pinned_ptr = None
             try:
                 from . import _native
 
@@ -92,8 +114,13 @@ class HdrImage:
             except Exception:
                 pass
 
+    def __del__(self):
+        self.unpin()
+
     @property
     def pixels(self) -> PixelView:
+        """A view: ``image.pixels[i] = color`` writes through, but the ``Color`` objects it yields are
+        copies (``image.pixels[i].r = x`` is lost — use ``set_pixel`` or assign the element)."""
         return PixelView(self._rgb)
 
     # -- reference interface
@@ -135,7 +162,10 @@ class HdrImage:
 
         tonemap.write_ldr_image(self, stream, format, gamma=gamma, flags=0)
 
-    def write_pfm(self, stream, little_endian: bool = True) -> None:
+    def write_pfm(self, stream, endianness=Endianness.LITTLE_ENDIAN, little_endian: Optional[bool] = None) -> None:
+        """hdrimages.py:96-118: ``write_pfm(stream, endianness=Endianness.LITTLE_ENDIAN)``; ``little_endian=``
+        is kept as a keyword alias."""
+        little_endian = _is_little_endian(endianness) if little_endian is None else bool(little_endian)
         stream.write(f"PF\n{self.width} {self.height}\n{'-1.0' if little_endian else '1.0'}\n".encode("ascii"))
         stream.write(self._rgb[::-1].astype("<f4" if little_endian else ">f4").tobytes())
 
@@ -178,9 +208,12 @@ def install_array(image, rgb: np.ndarray) -> None:
     a reference ``pytracer.hdrimages.HdrImage`` gets a :class:`PixelView` as its ``pixels`` (built
     on the reference's own ``Color`` type) — no per-pixel Python work in either case."""
     if isinstance(image, HdrImage):
+        if rgb is image._rgb:  # rendered straight into the image's own (page-locked) buffer
+            return
         if image._rgb.shape == rgb.shape and image._rgb.dtype == rgb.dtype:
             np.copyto(image._rgb, rgb)
         else:
+            image.unpin()  # never leave a registration on a buffer numpy is about to free
             image._rgb = np.ascontiguousarray(rgb)
         return
     color_type = Color

@@ -55,18 +55,27 @@ class CudaRenderer(Renderer):
         self.accel = accel  # "none": the reference's loop over all shapes; "bvh": sphere hierarchy (same image)
         self.last_stats: dict = {}
         self._scene: Optional[DeviceScene] = None
-        self._scene_key = None
 
-    # -- device scene, rebuilt when the world's shape / light lists change
+    # -- device scene: the reference's renderers read the World live at every call, so the world is
+    # flattened again for every image and compared with what is resident in HBM (bulk array compares)
     def device_scene(self) -> DeviceScene:
-        key = (id(self.world), len(self.world.shapes), len(getattr(self.world, "point_lights", [])))
-        if self._scene is None or key != self._scene_key:
-            self.refresh()
-            self._scene_key = key
+        """The resident device scene, brought up to date with ``self.world``: unchanged -> reused as is;
+        only transformations edited -> patched in place (rt_scene_update_transforms); anything else
+        (shapes added / replaced, materials, pigments, textures, lights edited) -> rebuilt."""
+        from .flatten import flatten_world
+
+        new = flatten_world(self.world)
+        if self._scene is None:
+            self._scene = DeviceScene(new)
+        elif not self._scene.flat.differs_only_in_transforms(new):
+            self._scene.close()
+            self._scene = DeviceScene(new)
+        elif not (np.array_equal(self._scene.flat.shape_m, new.shape_m) and np.array_equal(self._scene.flat.shape_invm, new.shape_invm)):
+            self._scene.update_from_world(new)
         return self._scene
 
     def refresh(self) -> None:
-        """Flatten and upload the world again (call after editing shapes in place)."""
+        """Flatten and upload the world again unconditionally."""
         if self._scene is not None:
             self._scene.close()
         self._scene = DeviceScene(self.world)
@@ -75,19 +84,9 @@ class CudaRenderer(Renderer):
         """Next frame of an animation (the reference re-parses the scene with another `clock`,
         main.py:122-128): if only transformations changed the resident device scene is patched in
         place (rt_scene_update_transforms), otherwise it is rebuilt.  Returns True when patched."""
-        from .flatten import flatten_world
-
+        had = self._scene
         self.world = world
-        key = (id(world), len(world.shapes), len(getattr(world, "point_lights", [])))
-        if self._scene is not None:
-            new = flatten_world(world)
-            if self._scene.flat.differs_only_in_transforms(new):
-                self._scene.update_from_world(new)
-                self._scene_key = key
-                return True
-        self.refresh()
-        self._scene_key = key
-        return False
+        return self.device_scene() is had
 
     def make_params(self, width: int, height: int, camera, samples_per_side: int = 0, aa_pcg: Optional[PCG] = None,
                     **overrides) -> _abi.rt_render_params:

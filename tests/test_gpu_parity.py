@@ -123,11 +123,17 @@ def test_demo_deterministic_vs_reference(algo, s, size):
     sc = DeviceScene(fs)
     p = make_params(size[0], size[1], cam, algo, s, aa_pcg=PCG(42, 54), out_f64=True)
     rgb, hit, stats = sc.render(p, want_hit=True)
-    assert stats["precision_used"] == _abi.RT_PRECISION_F64
+    # AUTO = the hybrid path (fp32 conservative gate + the reference's fp64 decisions); the plain fp64 kernel
+    # must give the very same image
+    assert stats["precision_used"] == _abi.RT_PRECISION_HYBRID
     assert np.array_equal(hit, g[f"hit_s{s}"])
     assert np.allclose(rgb, g[f"{algo}_s{s}_rgb"], rtol=1e-12, atol=1e-15)
     assert stats["rays_closest"] == int(g[f"{algo}_s{s}_rays_closest"])
     assert stats["rays_shadow"] == int(g[f"{algo}_s{s}_rays_shadow"])
+    p64 = make_params(size[0], size[1], cam, algo, s, aa_pcg=PCG(42, 54), out_f64=True, precision="f64")
+    rgb64, hit64, stats64 = sc.render(p64, want_hit=True)
+    assert stats64["precision_used"] == _abi.RT_PRECISION_F64
+    assert np.array_equal(rgb64, rgb) and np.array_equal(hit64, hit) and stats64["rays_shadow"] == stats["rays_shadow"]
     # fp32 arithmetic: same image up to edge pixels
     p32 = make_params(size[0], size[1], cam, algo, s, aa_pcg=PCG(42, 54), precision="f32")
     rgb32, hit32, _ = sc.render(p32, want_hit=True)
@@ -163,6 +169,99 @@ def test_config2_1080p_bit_exact_hit_index_and_colours():
         if algo != "onoff":
             assert_colors_close(rgb, g[f"{algo}_rgb_f32"], rel=REL)
         assert [stats["rays_closest"], stats["rays_shadow"]] == g[f"{algo}_rays"].tolist()
+
+
+# ------------------------------------------------------------------ hybrid precision (what AUTO resolves to)
+def _assert_hybrid_is_fp64(sc, cam, w, h, algo, S, **kw):
+    a, ha, sa = sc.render(make_params(w, h, cam, algo, S, aa_pcg=PCG(42, 54), out_f64=True, precision="f64", **kw), want_hit=True)
+    b, hb, sb = sc.render(make_params(w, h, cam, algo, S, aa_pcg=PCG(42, 54), out_f64=True, precision="hybrid", **kw), want_hit=True)
+    assert sb["precision_used"] == _abi.RT_PRECISION_HYBRID and sa["precision_used"] == _abi.RT_PRECISION_F64
+    assert np.array_equal(ha, hb), (algo, S, int((ha != hb).sum()))
+    assert np.array_equal(a, b), (algo, S, int((a != b).any(axis=-1).sum()))
+    assert (sa["rays_closest"], sa["rays_shadow"], sa["samples"]) == (sb["rays_closest"], sb["rays_shadow"], sb["samples"])
+    return sa, sb
+
+
+@pytest.mark.parametrize("n_spheres", [0, 1, 3, 37, 1100])
+def test_hybrid_gate_never_changes_the_fp64_image(n_spheres):
+    """RT_PRECISION_HYBRID (rt_resolve_hybrid.cuh): the fp32 gate only decides which spheres the fp64 code
+    looks at, and it is conservative — so hit index, colours (fp64 output) and shadow-ray counts must equal the
+    plain fp64 kernel's BIT FOR BIT: every renderer, 1 / 4 / 9 samples per pixel (one ray per sweep, four
+    per sweep, four with a remainder), odd image sizes, resident tables (<= 96 KB) and streamed ones
+    (1 100 spheres x 2 origins: two chunks per sweep), row and strata partitions."""
+    rs = scenes.random_spheres_scene(n_spheres, 2024, 4, 20.0, with_light=True)
+    sc = DeviceScene(flatten_world(rs.world))
+    w, h = (97, 61) if n_spheres > 100 else (67, 41)
+    for algo in ("onoff", "flat", "pointlight"):
+        for S in (0, 2, 3):
+            _assert_hybrid_is_fp64(sc, rs.camera, w, h, algo, S)
+    _assert_hybrid_is_fp64(sc, rs.camera, w, h, "pointlight", 2, part_mode=_abi.RT_PART_ROWS, part_rank=1, part_count=3)
+    _assert_hybrid_is_fp64(sc, rs.camera, w, h, "pointlight", 2, part_mode=_abi.RT_PART_SPP, part_rank=1, part_count=2)
+
+
+def test_hybrid_on_the_reference_scenes_and_awkward_geometry():
+    """demo.txt and the second golden scene (ellipsoids, image pigment, two lights) through the hybrid path
+    against the plain fp64 kernel; then geometry that stresses the gate's error bound: a camera inside a
+    sphere, a light inside a sphere, needle- and pancake-shaped ellipsoids (condition number 1e3), a scene
+    sitting 1e4 units from the world's origin (where the fp32 form M o + t has lost four digits), and spheres
+    seen from 1e5 radii away.  An orthogonal camera has no common ray origin: AUTO stays on the fp64 kernel."""
+    from pytracer_b200 import (Color, DiffuseBRDF, Material, PerspectiveCamera, Plane, Point, PointLight, Sphere,
+                               UniformPigment, Vec, World, rotation_x, rotation_z, scaling, translation)
+
+    fs, cam = demo_flat()
+    sc = DeviceScene(fs)
+    for algo in ("onoff", "flat", "pointlight"):
+        _assert_hybrid_is_fp64(sc, cam, 160, 120, algo, 2)
+    fs2, cam_p, cam_o = scene2_flat()
+    sc2 = DeviceScene(fs2)
+    for algo in ("onoff", "flat", "pointlight"):
+        _assert_hybrid_is_fp64(sc2, cam_p, 96, 64, algo, 2, background=(0.02, 0.03, 0.04))
+    _, _, st = sc2.render(make_params(32, 24, cam_o, "flat", 0))
+    assert st["precision_used"] == _abi.RT_PRECISION_F64
+    with pytest.raises(Exception):
+        sc2.render(make_params(32, 24, cam_o, "flat", 0, precision="hybrid"))
+
+    mat = Material(DiffuseBRDF(UniformPigment(Color(0.5, 0.6, 0.7))), UniformPigment(Color(0.1, 0.0, 0.0)))
+    for offset in (0.0, 1.0e4):
+        base = translation(Vec(offset, -offset, 0.0))
+        world = World()
+        world.add_shape(Sphere(base * scaling(Vec(30.0, 30.0, 30.0)), mat))                       # the camera is inside
+        world.add_shape(Sphere(base * translation(Vec(3.0, 0.0, 0.0)) * scaling(Vec(1e-3, 1.0, 1.0)), mat))  # pancake
+        world.add_shape(Sphere(base * translation(Vec(4.0, 1.0, 0.5)) * rotation_z(33.0) * rotation_x(71.0) * scaling(Vec(2.0, 2e-3, 2e-3)), mat))  # needle
+        world.add_shape(Sphere(base * translation(Vec(5.0, -1.0, 0.0)) * scaling(Vec(5e-5, 5e-5, 5e-5)), mat))  # 1e5 radii away
+        world.add_shape(Sphere(base * translation(Vec(2.0, 2.0, 2.0)) * scaling(Vec(0.5, 0.5, 0.5)), mat))   # the light is inside
+        for k in range(24):
+            world.add_shape(Sphere(base * translation(Vec(3.0 + 0.3 * k, 0.1 * k - 1.0, 0.2 * (k % 5) - 0.4)) * rotation_z(10.0 * k)
+                                   * scaling(Vec(0.05 + 0.01 * k, 0.3, 0.02 + 0.02 * (k % 7))), mat))
+        world.add_shape(Plane(base * translation(Vec(0.0, 0.0, -1.0)), mat))
+        world.add_light(PointLight(Point(offset + 2.0, -offset + 2.0, 2.0), Color(1.0, 1.0, 1.0)))
+        world.add_light(PointLight(Point(offset + 0.0, -offset - 3.0, 4.0), Color(0.5, 0.5, 0.5), 1.0))
+        cam = PerspectiveCamera(screen_distance=1.0, aspect_ratio=1.5, transformation=base * translation(Vec(-1.0, 0.0, 0.0)))
+        sc3 = DeviceScene(world)
+        for algo in ("onoff", "pointlight"):
+            sa, _ = _assert_hybrid_is_fp64(sc3, cam, 150, 100, algo, 2)
+        assert sa["rays_shadow"] > 0
+
+
+def test_config5_full_size_hybrid_equals_fp64():
+    """BASELINE config 5 at full size (4096 ellipsoids, pointlight, 3840x2160, 4 spp; 33.2 M samples):
+    the default precision (AUTO -> hybrid) gives the fp64 kernel's frame bit for bit — all 8.3 M hit indices
+    and 24.9 M colour values — several times faster, and a window of it equals the oracle."""
+    rs = scenes.random_spheres_scene(4096, 2025, 5, 40.0, with_light=True)
+    fs = flatten_world(rs.world)
+    sc = DeviceScene(fs)
+    a, ha, sa = sc.render(make_params(3840, 2160, rs.camera, "pointlight", 2, aa_pcg=PCG(42, 54), precision="f64"), want_hit=True)
+    b, hb, sb = sc.render(make_params(3840, 2160, rs.camera, "pointlight", 2, aa_pcg=PCG(42, 54)), want_hit=True)
+    assert sb["precision_used"] == _abi.RT_PRECISION_HYBRID
+    assert np.array_equal(ha, hb) and np.array_equal(a, b)
+    assert (sa["rays_closest"], sa["rays_shadow"]) == (sb["rays_closest"], sb["rays_shadow"])
+    print(f"config 5: fp64 {sa['kernel_ms']:.1f} ms, hybrid {sb['kernel_ms']:.1f} ms ({sa['kernel_ms'] / sb['kernel_ms']:.2f}x)")
+    assert sb["kernel_ms"] < 0.5 * sa["kernel_ms"]
+    # fp32 against the same frame: the measured hit-index mismatch rate of the pure-fp32 kernels
+    c, hc, _ = sc.render(make_params(3840, 2160, rs.camera, "pointlight", 2, aa_pcg=PCG(42, 54), precision="f32"), want_hit=True)
+    d, hd, _ = sc.render(make_params(3840, 2160, rs.camera, "pointlight", 2, aa_pcg=PCG(42, 54), precision="f32", accel="bvh"), want_hit=True)
+    print(f"config 5 fp32 hit-index mismatch vs fp64: linear {(hc != ha).mean():.2e}, bvh {(hd != ha).mean():.2e}, linear vs bvh {(hc != hd).mean():.2e}")
+    assert (hc != ha).mean() < 5e-4 and (hd != ha).mean() < 5e-4
 
 
 # ------------------------------------------------------------------ path tracing

@@ -138,6 +138,18 @@ def test_pfm_write_and_read_match_the_reference_bytes():
     big = io.BytesIO()
     img.write_pfm(big, little_endian=False)
     assert read_pfm_image(io.BytesIO(big.getvalue())).get_pixel(1, 1).is_close(Color(4.0e2, 5.0e2, 6.0e2))
+    # the reference's signature: write_pfm(stream, endianness=Endianness.LITTLE_ENDIAN), hdrimages.py:96
+    from pytracer_b200 import Endianness
+
+    for arg, want in ((Endianness.BIG_ENDIAN, big.getvalue()), (Endianness.LITTLE_ENDIAN, LE_REFERENCE_BYTES)):
+        out = io.BytesIO()
+        img.write_pfm(out, arg)
+        assert out.getvalue() == want
+        out = io.BytesIO()
+        img.write_pfm(out, endianness=arg)
+        assert out.getvalue() == want
+    with pytest.raises(TypeError):
+        img.write_pfm(io.BytesIO(), "big")
     with pytest.raises(InvalidPfmFileFormat):
         read_pfm_image(io.BytesIO(b"PF\n3 2\n-1.0\nstop"))
     assert img.pixel_offset(2, 1) == 5 and img.valid_coordinates(2, 1) and not img.valid_coordinates(3, 0)
