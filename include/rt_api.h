@@ -68,6 +68,14 @@ enum { RT_RNG_STREAMS = 0, RT_RNG_REPLAY = 1 };
  * does not own are zero), so one sum over ranks is the final image. */
 enum { RT_PART_NONE = 0, RT_PART_SPP = 1, RT_PART_ROWS = 2 };
 
+/* Where RT_PART_ROWS stores the rows a rank owns.  FULL: in place in a full-size image (the other rows are
+ * zero).  COMPACT: densely, [owned rows][width][3] — the slab an all-gather moves; rt_render() (host
+ * buffers) then copies the slab's rows to rows rank, rank + count, ... of the caller's FULL-SIZE host image
+ * and touches nothing else, so that ranks sharing one page-locked host image fill it together without any
+ * device-side exchange. */
+enum { RT_ROWS_FULL = 0, RT_ROWS_COMPACT = 1 };
+#define RT_MAX_PEERS 8
+
 /* Content of the optional int32[H][W] side image: the shape hit by the last sample of the pixel
  * (-1 = miss), or the number of rays (closest-hit + shadow queries) this rank traced for the
  * pixel — the divergence map of the scene. */
@@ -171,6 +179,14 @@ typedef struct rt_render_params {
   int32_t out_f64;          /* 1: out_rgb is double[H][W][3] instead of float */
   int32_t hit_mode;         /* what out_hit_index receives: RT_HIT_SHAPE or RT_HIT_RAY_COUNT */
   int32_t accel;            /* RT_ACCEL_*: how World.ray_intersection / is_point_visible find their shapes */
+  int32_t rows_layout;      /* RT_ROWS_* (RT_PART_ROWS only) */
+  /* n_peer_images > 0 (rt_render_device, RT_PART_ROWS, RT_ROWS_FULL, fp32 image): the render kernel stores
+   * every finished pixel into ALL of peer_images[0 .. n) — full-size images of the ranks of one node,
+   * mapped into this process (CUDA IPC / symmetric memory; peer_images[part_rank] is this rank's own) —
+   * instead of d_out_rgb: the exchange of the row split happens inside the kernel, pixel by pixel over
+   * NVLink, and needs no collective afterwards (only a barrier before anyone reads). */
+  int32_t n_peer_images;
+  void* peer_images[RT_MAX_PEERS];
 } rt_render_params;
 
 typedef struct rt_stats {
@@ -308,6 +324,9 @@ int rt_host_unregister(void* ptr);
  * Runs a register-resident FFMA chain kernel (8 independent accumulators per thread, grid sized to
  * fill every SM) and reports achieved TFLOP/s (2 flops per FMA) and the kernel time. */
 int rt_bench_ffma(int32_t iterations, double* tflops, float* ms);
+/* Same with DFMA chains: the denominator for the fp64 share of the F64 / HYBRID kernels (which, compiled
+ * without multiply-add fusion like the reference's arithmetic, can reach half of it in flops). */
+int rt_bench_dfma(int32_t iterations, double* tflops, float* ms);
 
 #ifdef __cplusplus
 }

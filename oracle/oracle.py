@@ -28,7 +28,9 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     """gcc -O2 -ffp-contract=off (no fused multiply-add: Python never fuses)."""
-    if force or not _LIB.exists() or _LIB.stat().st_mtime < _SRC.stat().st_mtime:
+    header = _HERE.parent / "include" / "rt_api.h"  # the structs the oracle shares with the library
+    newest = max(_SRC.stat().st_mtime, header.stat().st_mtime if header.exists() else 0.0)
+    if force or not _LIB.exists() or _LIB.stat().st_mtime < newest:
         cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-o", str(_LIB), str(_SRC), "-lm"]
         subprocess.run(cmd, check=True)
     return _LIB

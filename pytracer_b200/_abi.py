@@ -19,6 +19,8 @@ RT_RNG_STREAMS, RT_RNG_REPLAY = 0, 1
 RT_PART_NONE, RT_PART_SPP, RT_PART_ROWS = 0, 1, 2
 RT_HIT_SHAPE, RT_HIT_RAY_COUNT = 0, 1
 PARTITIONS = {"none": 0, "spp": 1, "rows": 2}
+RT_ROWS_FULL, RT_ROWS_COMPACT = 0, 1
+RT_MAX_PEERS = 8
 ACCELS = {"none": 0, "bvh": 1}  # RT_ACCEL_*
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_NO_DEVICE, RT_ERR_OVERFLOW = 0, -1, -2, -3, -4
@@ -107,6 +109,9 @@ class rt_render_params(C.Structure):
         ("out_f64", C.c_int32),
         ("hit_mode", C.c_int32),
         ("accel", C.c_int32),
+        ("rows_layout", C.c_int32),
+        ("n_peer_images", C.c_int32),
+        ("peer_images", C.c_void_p * 8),
     ]
 
 

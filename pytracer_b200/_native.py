@@ -48,6 +48,7 @@ _PROTOTYPES = {
     "rt_host_register": (C.c_int, [_P, C.c_uint64]),
     "rt_host_unregister": (C.c_int, [_P]),
     "rt_bench_ffma": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "rt_bench_dfma": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 

@@ -69,6 +69,7 @@ struct rt_scene {
   void* arena = nullptr;  // ONE device allocation holding every table below
   float *invm32 = nullptr, *m32 = nullptr, *packed32 = nullptr;
   int n_pairs = 0;
+  float gate_a = 0.f, gate_t = 0.f;  // slack of the fp32 sweep's gate (rt_device.cuh pack_ray)
   double *invm64 = nullptr, *m64 = nullptr;
   int32_t *orig = nullptr, *material = nullptr;
   DevMaterial* materials = nullptr;
@@ -91,6 +92,8 @@ struct rt_scene {
   int last_precision = 0;
   bool pending = false;
 };
+
+static void set_gate_constants(rt_scene* s);
 
 static int get_workspace(int device, Workspace** out) {
   static Workspace* table[64] = {nullptr};
@@ -137,9 +140,9 @@ template <> SceneView<float> view_of<float>(const rt_scene* s) {
   v.invm = s->invm32; v.m = s->m32; v.orig = s->orig; v.material = s->material;
   v.materials = s->materials; v.pigments = s->pigments; v.lights = s->lights;
   v.n_shapes = s->n_shapes; v.n_spheres = s->n_spheres; v.n_lights = s->n_lights;
-  v.packed = s->packed32; v.n_pairs = s->n_pairs; v._pad = 0;
+  v.packed = s->packed32; v.n_pairs = s->n_pairs; v.gate_a = s->gate_a;
   v.n_materials = s->n_materials; v.n_pigments = s->n_pigments;
-  v.bvh_nodes = (const float4*)s->bvh_nodes; v.bvh_prims = s->bvh_prims; v.accel = 0; v._pad2 = 0;
+  v.bvh_nodes = (const float4*)s->bvh_nodes; v.bvh_prims = s->bvh_prims; v.accel = 0; v.gate_t = s->gate_t;
   return v;
 }
 template <> SceneView<double> view_of<double>(const rt_scene* s) {
@@ -147,9 +150,9 @@ template <> SceneView<double> view_of<double>(const rt_scene* s) {
   v.invm = s->invm64; v.m = s->m64; v.orig = s->orig; v.material = s->material;
   v.materials = s->materials; v.pigments = s->pigments; v.lights = s->lights;
   v.n_shapes = s->n_shapes; v.n_spheres = s->n_spheres; v.n_lights = s->n_lights;
-  v.packed = nullptr; v.n_pairs = 0; v._pad = 0;
+  v.packed = nullptr; v.n_pairs = 0; v.gate_a = 0.f;
   v.n_materials = s->n_materials; v.n_pigments = s->n_pigments;
-  v.bvh_nodes = (const float4*)s->bvh_nodes; v.bvh_prims = s->bvh_prims; v.accel = 0; v._pad2 = 0;
+  v.bvh_nodes = (const float4*)s->bvh_nodes; v.bvh_prims = s->bvh_prims; v.accel = 0; v.gate_t = 0.f;
   return v;
 }
 
@@ -229,6 +232,7 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
   s->sorted_of_orig.assign(d->n_shapes, 0);
   for (int j = 0; j < d->n_shapes; ++j) s->sorted_of_orig[orig[j]] = j;
   s->h_invm32 = invm32; s->h_m32 = m32; s->h_invm64 = invm64; s->h_m64 = m64; s->h_packed = packed;
+  set_gate_constants(s);
 
   // ---- textures: fp64 copy for the fp64 path, float4 CUDA arrays behind texture objects for fp32
   std::vector<double> tex64;
@@ -334,6 +338,25 @@ extern "C" int rt_scene_create(const rt_scene_desc* d, rt_scene** out) {
   return RT_OK;
 }
 
+// Constants of the fp32 sweep's gate (rt_device.cuh pack_ray): sqrt(8 u) times the largest Frobenius norm of
+// a sphere's inverse 3x3 block and the largest norm of its translation column.
+static void set_gate_constants(rt_scene* s) {
+  double a_max = 0.0, t_max = 0.0;
+  for (int i = 0; i < s->n_spheres; ++i) {
+    const double* m = s->h_invm64.data() + 12 * (size_t)i;
+    double f = 0.0, t = 0.0;
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) f += m[4 * r + c] * m[4 * r + c];
+      t += m[4 * r + 3] * m[4 * r + 3];
+    }
+    a_max = std::max(a_max, std::sqrt(f));
+    t_max = std::max(t_max, std::sqrt(t));
+  }
+  const double k = std::sqrt(8.0 * 5.9604644775390625e-08);
+  s->gate_a = std::isfinite(a_max) ? (float)(k * a_max) : 0.f;
+  s->gate_t = std::isfinite(t_max) ? (float)(k * t_max) : 0.f;
+}
+
 // Animation (the reference re-parses the scene per frame with `-d clock:VALUE`,
 // scene_file.py:654-675 / main.py:122-128): only Transformation.m / .invm of some shapes change between
 // frames, so the resident scene is patched in place — 336 B per shape over five tables — instead of
@@ -360,6 +383,7 @@ extern "C" int rt_scene_update_transforms(rt_scene* s, int32_t first, int32_t n,
   CU(cudaMemcpyAsync(s->invm64, s->h_invm64.data(), s->h_invm64.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(s->m64, s->h_m64.data(), s->h_m64.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(s->packed32, s->h_packed.data(), s->h_packed.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  set_gate_constants(s);
   s->bvh_valid = false;  // rebuilt by the next render that asks for it
   return RT_OK;
 }
@@ -395,16 +419,34 @@ static int fill_args(const rt_scene* s, const rt_render_params* p, RenderArgs* a
   a->part_rank = p->part_rank; a->part_count = p->part_count > 1 ? p->part_count : 1;
   a->out_f64 = p->out_f64 ? 1 : 0;
   a->hit_mode = p->hit_mode;
+  if (p->rows_layout != RT_ROWS_FULL && p->rows_layout != RT_ROWS_COMPACT) return fail(RT_ERR_INVALID, "rows_layout %d", p->rows_layout);
+  a->rows_compact = (a->part_mode == RT_PART_ROWS && p->rows_layout == RT_ROWS_COMPACT) ? 1 : 0;
+  a->n_peers = 0;
+  if (p->n_peer_images != 0) {
+    if (p->n_peer_images < 0 || p->n_peer_images > RT_MAX_PEERS) return fail(RT_ERR_INVALID, "n_peer_images %d", p->n_peer_images);
+    if (a->part_mode != RT_PART_ROWS || a->rows_compact || a->out_f64 || p->n_peer_images != a->part_count)
+      return fail(RT_ERR_INVALID, "peer_images need RT_PART_ROWS, RT_ROWS_FULL, an fp32 image and one image per rank");
+    for (int k = 0; k < p->n_peer_images; ++k) {
+      if (!p->peer_images[k]) return fail(RT_ERR_INVALID, "peer_images[%d] is null", k);
+      a->peer_out[k] = (float*)p->peer_images[k];
+    }
+    a->n_peers = p->n_peer_images;
+  }
   a->counters = s->ws->counters;
   build_jump_table(p->aa_inc, &a->jump);
   return RT_OK;
 }
 
+// rows of the image this rank traces (RT_PART_ROWS: rank, rank + count, ...)
+static long long owned_rows(const RenderArgs& a) {
+  long long rows = a.height;
+  if (a.part_mode == RT_PART_ROWS && a.part_count > 1) rows = (a.height - a.part_rank + a.part_count - 1) / a.part_count;
+  return std::max(rows, 0ll);
+}
 // samples (Renderer.__call__ invocations) this rank's share of the image holds
 static long long make_pixel_count(const RenderArgs& a) {
   long long S2 = a.S > 0 ? (long long)a.S * a.S : 1;
-  long long rows = a.height, strata = S2;
-  if (a.part_mode == RT_PART_ROWS && a.part_count > 1) rows = (a.height - a.part_rank + a.part_count - 1) / a.part_count;
+  long long rows = owned_rows(a), strata = S2;
   if (a.part_mode == RT_PART_SPP && a.part_count > 1) strata = a.part_rank < S2 ? (S2 - a.part_rank + a.part_count - 1) / a.part_count : 0;
   return std::max(rows, 0ll) * a.width * strata;
 }
@@ -455,7 +497,7 @@ static int ensure_bvh(rt_scene* s, cudaStream_t st) {
 }
 
 extern "C" int rt_render_device(rt_scene* s, const rt_render_params* p, void* d_out_rgb, int32_t* d_out_hit, void* stream) {
-  if (!s || !p || !d_out_rgb) return fail(RT_ERR_INVALID, "rt_render_device: null argument");
+  if (!s || !p || (!d_out_rgb && p->n_peer_images <= 0)) return fail(RT_ERR_INVALID, "rt_render_device: null argument");
   CU(cudaSetDevice(s->device));
   cudaStream_t st = (cudaStream_t)stream;
   RenderArgs a;
@@ -489,10 +531,12 @@ extern "C" int rt_render_device(rt_scene* s, const rt_render_params* p, void* d_
       a.replay = s->ws->replay;
     }
   }
-  size_t px = (size_t)p->width * p->height;
+  // pixels of the device image: the whole frame, or only the rows this rank owns (RT_ROWS_COMPACT)
+  size_t px = (size_t)p->width * (a.rows_compact ? (size_t)owned_rows(a) : (size_t)p->height);
+  if (a.n_peers > 0 && pt && p->max_depth < 0) return fail(RT_ERR_INVALID, "peer_images with max_depth < 0");
   CU(cudaMemsetAsync(s->ws->counters, 0, CNT_SLOTS * sizeof(unsigned long long), st));
   // rows this rank does not own stay zero, so that a sum over ranks is the image
-  const bool partial_rows = a.part_mode == RT_PART_ROWS;
+  const bool partial_rows = a.part_mode == RT_PART_ROWS && !a.rows_compact && a.n_peers == 0;
   long long S2 = p->samples_per_side > 0 ? (long long)p->samples_per_side * p->samples_per_side : 1;
   const bool no_strata = a.part_mode == RT_PART_SPP && a.part_rank >= S2;
   if (partial_rows || no_strata) {
@@ -577,17 +621,34 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, void* out_rgb, 
   if (!s || !p || !out_rgb) return fail(RT_ERR_INVALID, "rt_render: null argument");
   CU(cudaSetDevice(s->device));
   if (p->width <= 0 || p->height <= 0) return fail(RT_ERR_INVALID, "image size %dx%d", p->width, p->height);
-  size_t px = (size_t)p->width * p->height;
-  size_t bytes = px * 3 * (p->out_f64 ? sizeof(double) : sizeof(float));
+  if (p->n_peer_images != 0) return fail(RT_ERR_INVALID, "peer_images belong to rt_render_device");
+  // RT_ROWS_COMPACT: the device image holds this rank's rows only; they are copied to their places in the
+  // caller's full-size host image (which other ranks may be filling at the same time: shared page-locked memory)
+  const bool compact = p->part_mode == RT_PART_ROWS && p->part_count > 1 && p->rows_layout == RT_ROWS_COMPACT;
+  if (compact && (p->part_rank < 0 || p->part_rank >= p->part_count)) return fail(RT_ERR_INVALID, "partition rank %d of %d", p->part_rank, p->part_count);
+  const size_t rows = compact ? (size_t)((p->height - p->part_rank + p->part_count - 1) / p->part_count) : (size_t)p->height;
+  const size_t px = (size_t)p->width * rows;
+  const size_t px_bytes = 3 * (p->out_f64 ? sizeof(double) : sizeof(float));
+  const size_t bytes = px * px_bytes;
   int rc;
-  if ((rc = ensure(&s->ws->image, &s->ws->image_cap, bytes)) != RT_OK) return rc;
-  if (out_hit && (rc = ensure((void**)&s->ws->hit, &s->ws->hit_cap, px * sizeof(int32_t))) != RT_OK) return rc;
+  if ((rc = ensure(&s->ws->image, &s->ws->image_cap, std::max<size_t>(bytes, 16))) != RT_OK) return rc;
+  if (out_hit && (rc = ensure((void**)&s->ws->hit, &s->ws->hit_cap, std::max<size_t>(px * sizeof(int32_t), 16))) != RT_OK) return rc;
   cudaEvent_t t0 = s->ws->t0, t1 = s->ws->t1;
   CU(cudaEventRecord(t0, 0));
   rc = rt_render_device(s, p, s->ws->image, out_hit ? s->ws->hit : nullptr, nullptr);
   if (rc == RT_OK) {
-    cudaError_t e = cudaMemcpyAsync(out_rgb, s->ws->image, bytes, cudaMemcpyDeviceToHost, 0);
-    if (e == cudaSuccess && out_hit) e = cudaMemcpyAsync(out_hit, s->ws->hit, px * sizeof(int32_t), cudaMemcpyDeviceToHost, 0);
+    cudaError_t e = cudaSuccess;
+    if (!compact) {
+      e = cudaMemcpyAsync(out_rgb, s->ws->image, bytes, cudaMemcpyDeviceToHost, 0);
+      if (e == cudaSuccess && out_hit) e = cudaMemcpyAsync(out_hit, s->ws->hit, px * sizeof(int32_t), cudaMemcpyDeviceToHost, 0);
+    } else if (rows > 0) {
+      const size_t row_bytes = (size_t)p->width * px_bytes, hit_row = (size_t)p->width * sizeof(int32_t);
+      e = cudaMemcpy2DAsync((char*)out_rgb + (size_t)p->part_rank * row_bytes, (size_t)p->part_count * row_bytes, s->ws->image, row_bytes,
+                            row_bytes, rows, cudaMemcpyDeviceToHost, 0);
+      if (e == cudaSuccess && out_hit)
+        e = cudaMemcpy2DAsync((char*)out_hit + (size_t)p->part_rank * hit_row, (size_t)p->part_count * hit_row, s->ws->hit, hit_row, hit_row,
+                              rows, cudaMemcpyDeviceToHost, 0);
+    }
     if (e == cudaSuccess) e = cudaEventRecord(t1, 0);
     if (e != cudaSuccess) rc = fail(RT_ERR_CUDA, "image copy: %s", cudaGetErrorString(e));
   }
@@ -762,22 +823,23 @@ extern "C" int rt_camera_fire(const rt_camera* cam, int32_t precision, const dou
                    (size_t)n * 8 * sizeof(double), 0);
 }
 
-extern "C" int rt_bench_ffma(int32_t iterations, double* tflops, float* ms_out) {
+// FMA throughput probes (fp64 = 0: FFMA, 1: DFMA): 8 independent chains per thread, 2048 threads per SM
+static int bench_fma(int fp64, int32_t iterations, double* tflops, float* ms_out) {
   if (rt_device_count() <= 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
   if (iterations < 1) iterations = 1;
-  int dev = 0;
+  int dev = 0, sms = 0;
   CU(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, dev));
-  const int blocks = prop.multiProcessorCount * 8;  // 2048 threads per SM
-  float* out = nullptr;
-  CU(cudaMalloc((void**)&out, (size_t)blocks * 256 * sizeof(float)));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8;
+  void* out = nullptr;
+  CU(cudaMalloc(&out, (size_t)blocks * 256 * sizeof(double)));
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0));
   CU(cudaEventCreate(&e1));
-  cudaError_t e = launch_ffma(out, blocks, iterations, 0);  // warm-up
+  auto launch = [&]() { return fp64 ? launch_dfma((double*)out, blocks, iterations, 0) : launch_ffma((float*)out, blocks, iterations, 0); };
+  cudaError_t e = launch();  // warm-up
   if (e == cudaSuccess) e = cudaEventRecord(e0, 0);
-  if (e == cudaSuccess) e = launch_ffma(out, blocks, iterations, 0);
+  if (e == cudaSuccess) e = launch();
   if (e == cudaSuccess) e = cudaEventRecord(e1, 0);
   if (e == cudaSuccess) e = cudaEventSynchronize(e1);
   float ms = 0.f;
@@ -785,12 +847,14 @@ extern "C" int rt_bench_ffma(int32_t iterations, double* tflops, float* ms_out) 
   cudaFree(out);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  if (e != cudaSuccess) return fail(RT_ERR_CUDA, "rt_bench_ffma: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, "FMA probe: %s", cudaGetErrorString(e));
   double flops = (double)blocks * 256.0 * (double)iterations * 16.0 * 8.0 * 2.0;
   if (tflops) *tflops = flops / (ms * 1e-3) / 1e12;
   if (ms_out) *ms_out = ms;
   return RT_OK;
 }
+extern "C" int rt_bench_ffma(int32_t iterations, double* tflops, float* ms) { return bench_fma(0, iterations, tflops, ms); }
+extern "C" int rt_bench_dfma(int32_t iterations, double* tflops, float* ms) { return bench_fma(1, iterations, tflops, ms); }
 
 // ------------------------------------------------------------------------------------ tone mapping
 static int tonemap_workspace(Workspace** out) {

@@ -52,12 +52,15 @@ template <typename T> struct SceneView {
   int32_t n_shapes, n_spheres, n_lights;
   // fp32 only: [n_pairs][24] element-interleaved sphere pairs followed by [n_planes][12] planes
   const float* packed;
-  int32_t n_pairs, _pad;
+  int32_t n_pairs;
+  float gate_a;  // see pack_ray: sqrt(8 u) max_i |M_i|_F over the spheres
+
   int32_t n_materials, n_pigments;
   // sphere hierarchy (rt_bvh.cuh), used when accel != 0
   const float4* bvh_nodes;
   const int32_t* bvh_prims;
-  int32_t accel, _pad2;
+  int32_t accel;
+  float gate_t;  // sqrt(8 u) max_i |t_i| (translation column of the inverse transforms)
 };
 
 template <typename T> struct Hit {
@@ -215,13 +218,26 @@ RT_DEV f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1
 RT_DEV f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 RT_DEV f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
+// The sweep's gate delta/4 = (o'.d')^2 - a (|o'|^2 - 1) > 0 is evaluated in fp32 and every decision about a
+// sphere is then taken by sphere_cross on the spheres that pass, so the gate must not LOSE spheres: a
+// symmetric rounding noise in delta would turn into a bias (spheres that pass by noise are thrown out again
+// by sphere_cross, spheres that fail by noise are gone — every sphere would shrink by the noise band, and an
+// image of small far spheres comes out measurably brighter).  The noise is dominated by the cancellation in
+// o' = M o + t: |delta error| / a <~ 4 |o'| 5u (|M|_F |o| + |t|), at most 20u (|M|_F |o| + |t|)^2.  So the
+// gate tests against a sphere of radius^2 1 + s with s = 8u (A |o| + T)^2, A = max |M_i|_F, T = max |t_i| over
+// the scene (about four standard deviations of the observed noise; not a proof — the renderers whose hit
+// index must be exact take the rigorous gate of rt_resolve_hybrid.cuh).  It costs nothing: the constant -1
+// of the |o'|^2 - 1 chain becomes the per-ray value -(1 + s).
 struct PackedRay {  // ray components as broadcast pairs (the compiler turns them into .F32 scalar operands)
-  f32x2 ox, oy, oz, dx, dy, dz;
+  f32x2 ox, oy, oz, dx, dy, dz, k0;
 };
-RT_DEV PackedRay pack_ray(const Ray<float>& r) {
+RT_DEV PackedRay pack_ray(const Ray<float>& r, float gate_a, float gate_t) {
   PackedRay q;
   q.ox = pk2(r.o.x, r.o.x); q.oy = pk2(r.o.y, r.o.y); q.oz = pk2(r.o.z, r.o.z);
   q.dx = pk2(r.d.x, r.d.x); q.dy = pk2(r.d.y, r.d.y); q.dz = pk2(r.d.z, r.d.z);
+  const float w = fmaf(gate_a, fast_sqrt(fmaf(r.o.x, r.o.x, fmaf(r.o.y, r.o.y, r.o.z * r.o.z))), gate_t);
+  const float k = -fmaf(w, w, 1.0f);
+  q.k0 = pk2(k, k);
   return q;
 }
 
@@ -239,7 +255,7 @@ RT_DEV f32x2 pair_qdelta(const float4* __restrict__ q, const PackedRay& r) {
   const f32x2 dz = fma2(m20, r.dx, fma2(m21, r.dy, mul2(m22, r.dz)));
   const f32x2 a = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));
   const f32x2 hb = fma2(px, dx, fma2(py, dy, mul2(pz, dz)));
-  const f32x2 c = fma2(px, px, fma2(py, py, fma2(pz, pz, pk2(-1.0f, -1.0f))));
+  const f32x2 c = fma2(px, px, fma2(py, py, fma2(pz, pz, r.k0)));
   return sub2(mul2(hb, hb), mul2(a, c));
 }
 
@@ -299,7 +315,7 @@ RT_DEV void pair_qdelta2(const float4* __restrict__ q, const PackedRay& r0, cons
     const f32x2 dz = fma2(m20, r.dx, fma2(m21, r.dy, mul2(m22, r.dz)));                \
     const f32x2 a = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));                          \
     const f32x2 hb = fma2(px, dx, fma2(py, dy, mul2(pz, dz)));                         \
-    const f32x2 c = fma2(px, px, fma2(py, py, fma2(pz, pz, pk2(-1.0f, -1.0f))));       \
+    const f32x2 c = fma2(px, px, fma2(py, py, fma2(pz, pz, r.k0)));                    \
     out = sub2(mul2(hb, hb), mul2(a, c));                                              \
   }
   RT_QD(r0, qd0)
@@ -308,10 +324,10 @@ RT_DEV void pair_qdelta2(const float4* __restrict__ q, const PackedRay& r0, cons
 }
 
 RT_DEV void sweep_pairs2(const float4* __restrict__ pairs, int base, int p0, int p1, const Ray<float>& ray0,
-                         const Ray<float>& ray1, int* cand0, int& nc0, int* cand1, int& nc1) {
+                         const Ray<float>& ray1, float gate_a, float gate_t, int* cand0, int& nc0, int* cand1, int& nc1) {
   // the broadcast pairs are rebuilt here from the scalar rays: the compiler turns them into scalar
   // (.F32) operands of FFMA2, so they cost no registers outside the loop
-  const PackedRay r0 = pack_ray(ray0), r1 = pack_ray(ray1);
+  const PackedRay r0 = pack_ray(ray0, gate_a, gate_t), r1 = pack_ray(ray1, gate_a, gate_t);
   for (int p = p0; p < p1; ++p) {
     f32x2 q0, q1;
     pair_qdelta2(pairs + 6 * (p - base), r0, r1, q0, q1);
@@ -335,7 +351,8 @@ RT_DEV void sweep_pairs2(const float4* __restrict__ pairs, int base, int p0, int
 // sweep the partner's candidates are handed back with shuffles and merged in ascending sphere order.
 // Must be called by all 32 lanes (idle lanes pass a zero ray: a = 0, delta = 0, never crossed);
 // n_pairs is even (rt_scene_create pads the pair list).
-RT_DEV void sweep_pairs_split(const float4* __restrict__ pairs, int n_pairs, const Ray<float>& mine, int* cand, int& nc) {
+RT_DEV void sweep_pairs_split(const float4* __restrict__ pairs, int n_pairs, const Ray<float>& mine, float gate_a, float gate_t,
+                              int* cand, int& nc) {
   const unsigned FULL = 0xffffffffu;
   const bool hi = (threadIdx.x & 16) != 0;
   Ray<float> other;
@@ -346,7 +363,7 @@ RT_DEV void sweep_pairs_split(const float4* __restrict__ pairs, int n_pairs, con
   const int first = hi ? half : 0;
   int theirs[RT_CAND_CAP];
   int n_mine = 0, n_theirs = 0;
-  sweep_pairs2(pairs, 0, first, first + half, mine, other, cand, n_mine, theirs, n_theirs);
+  sweep_pairs2(pairs, 0, first, first + half, mine, other, gate_a, gate_t, cand, n_mine, theirs, n_theirs);
   // hand the partner's candidates back; the low half's spheres come first in the merged list
   const int n_recv = __shfl_xor_sync(FULL, n_theirs, 16);
   int merged[RT_CAND_CAP];
@@ -478,7 +495,7 @@ RT_DEV void closest_all_warp(const SceneView<float>& sc, const ScanSrc<float>& s
                              float& best_t, int& best, int origin) {
   int cand[RT_CAND_CAP];
   int nc = 0;
-  if (sc.n_pairs > 0) sweep_pairs_split(src.pairs, sc.n_pairs, r, cand, nc);
+  if (sc.n_pairs > 0) sweep_pairs_split(src.pairs, sc.n_pairs, r, sc.gate_a, sc.gate_t, cand, nc);
   if (live) {
     resolve_candidates(sc.invm, sc.n_spheres, cand, nc, r, best_t, best, origin);
     scan_plane_block(src.planes, sc.n_spheres, sc.n_shapes - sc.n_spheres, sc.orig, r, best_t, best, origin);
@@ -527,7 +544,7 @@ RT_DEV void closest_all_f32(const SceneView<float>& sc, const ScanSrc<float>& sr
   if (sc.n_pairs > 0) {
     int cand[RT_CAND_CAP];
     int nc = 0;
-    const PackedRay pr = pack_ray(r);
+    const PackedRay pr = pack_ray(r, sc.gate_a, sc.gate_t);
     sweep_pairs<UNROLL2>(src.pairs, 0, 0, sc.n_pairs, pr, cand, nc);
     resolve_candidates(sc.invm, sc.n_spheres, cand, nc, r, best_t, best, origin);
   }
@@ -548,7 +565,7 @@ template <> RT_DEV bool any_all<float>(const SceneView<float>& sc, const ScanSrc
   if (sc.n_pairs == 0) return false;
   int cand[RT_CAND_CAP];
   int nc = 0;
-  const PackedRay pr = pack_ray(r);
+  const PackedRay pr = pack_ray(r, sc.gate_a, sc.gate_t);
   sweep_pairs(src.pairs, 0, 0, sc.n_pairs, pr, cand, nc);
   return any_candidate_blocks(sc.invm, sc.n_spheres, cand, nc, r);
 }

@@ -24,7 +24,10 @@ template <typename T> RT_DEV V3<T> load3(const double* p) { return mk3<T>((T)p[0
 // ---------------------------------------------------------------- pixel ownership
 struct PixelMap {
   long long n_pixels;  // pixels this rank traces
-  int width, rank, count, rows_mode;
+  int width, rank, count, rows_mode, compact;
+  // where pixel p = (col, row) of this rank's share is stored: its place in the full-size image, or — row
+  // partition with RT_ROWS_COMPACT — in the dense [owned rows][width] image of this rank
+  RT_DEV long long at(long long p, int col, int row) const { return compact ? p : (long long)row * width + col; }
   RT_DEV void locate(long long p, int& col, int& row) const {
     int lrow;
     if (n_pixels < 0x7fffffffLL) {  // (uniform) a 64-bit division is ~100 instructions
@@ -44,6 +47,7 @@ __host__ __device__ inline PixelMap make_pixel_map(const RenderArgs& a) {
   pm.rows_mode = (a.part_mode == RT_PART_ROWS && a.part_count > 1);
   pm.rank = a.part_rank;
   pm.count = a.part_count;
+  pm.compact = pm.rows_mode && a.rows_compact;
   int rows = a.height;
   if (pm.rows_mode) rows = (a.height - a.part_rank + a.part_count - 1) / a.part_count;
   if (rows < 0) rows = 0;
@@ -56,7 +60,12 @@ RT_DEV bool stratum_is_mine(const RenderArgs& a, int s) {
 }
 
 template <typename T> RT_DEV void store_pixel(const RenderArgs& a, long long off, V3<T> c) {
-  if (a.out_f64) {
+  if (a.n_peers > 0) {  // row split with the exchange folded into the kernel: the pixel goes to every rank's image
+    for (int k = 0; k < a.n_peers; ++k) {
+      float* o = a.peer_out[k] + 3 * off;
+      o[0] = (float)c.x; o[1] = (float)c.y; o[2] = (float)c.z;
+    }
+  } else if (a.out_f64) {
     double* o = (double*)a.out_rgb + 3 * off;
     o[0] = (double)c.x; o[1] = (double)c.y; o[2] = (double)c.z;
   } else {
@@ -193,7 +202,7 @@ k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
       int cand[RT_CAND_CAP];
       int nc = 0;
       PackedRay pr;
-      if (mine) pr = pack_ray(ray);
+      if (mine) pr = pack_ray(ray, sc.gate_a, sc.gate_t);
       if (single) {
         if (mine) sweep_pairs(sh_pairs, 0, 0, sc.n_pairs, pr, cand, nc);
       } else {
@@ -248,7 +257,7 @@ k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
           int cand[RT_CAND_CAP];
           int nc = 0;
           PackedRay pr;
-          if (need) { pr = pack_ray(sr); blocked = any_plane_blocks(planes, n_planes, sr); }
+          if (need) { pr = pack_ray(sr, sc.gate_a, sc.gate_t); blocked = any_plane_blocks(planes, n_planes, sr); }
           if (single) {
             if (need && !blocked) sweep_pairs(sh_pairs, 0, 0, sc.n_pairs, pr, cand, nc);
           } else if (__syncthreads_or(need && !blocked)) {
@@ -281,8 +290,8 @@ k_resolve(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
   }
   if (active) {
     if (a.S > 0) cum = ((T)1 / (T)(S2)) * cum;  // imagetracer.py:99-101
-    store_pixel<T>(a, pix, cum);
-    if (a.out_hit) a.out_hit[pix] = a.hit_mode == RT_HIT_RAY_COUNT ? (int)(n_closest + n_shadow) : last_hit;
+    store_pixel<T>(a, pm.at(p, col, row), cum);
+    if (a.out_hit) a.out_hit[pm.at(p, col, row)] = a.hit_mode == RT_HIT_RAY_COUNT ? (int)(n_closest + n_shadow) : last_hit;
   }
   block_count_add(a.counters + CNT_CLOSEST, n_closest);
   block_count_add(a.counters + CNT_SHADOW, n_shadow);
@@ -442,7 +451,9 @@ k_pt_mega(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
     Pcg aa;
     aa.inc = a.aa_inc;
     aa.state = (a.S > 0) ? pcg_jump(a.aa_state, 2ull * (unsigned long long)pix * S2, a.jump) : 0;
-    V3<T> cum = mk3<T>((T)0, (T)0, (T)0);
+    // the pixel's sum over its strata is kept in fp64 whatever T is: a sequential fp32 sum of 1 024 equal
+    // samples (a sky pixel at 1 024 spp) is off by 3e-5, and it costs three additions per SAMPLE
+    V3<double> cum = mk3<double>(0.0, 0.0, 0.0);
     int last_hit = -1;
     for (int s = 0; s < S2; ++s) {
       Ray<T> ray = primary_ray<T>(a, col, row, s, aa);
@@ -451,13 +462,16 @@ k_pt_mega(const __grid_constant__ SceneView<T> sc, const __grid_constant__ Rende
       Pcg rng;
       if (a.rng_mode == RT_RNG_REPLAY) { rng.state = a.replay[k]; rng.inc = a.pt_inc; }
       else rng = pcg_seed(a.pt_state, (a.pt_inc >> 1) + k);
-      V3<T> c = pt_radiance<T, MAXL, BVH>(cx, ray, 0, rng, &last_hit);
-      cum = (a.S > 0) ? cum + c : c;
+      const V3<double> c = cast3<double>(pt_radiance<T, MAXL, BVH>(cx, ray, 0, rng, &last_hit));
+      cum = (a.S > 0) ? mk3<double>(__dadd_rn(cum.x, c.x), __dadd_rn(cum.y, c.y), __dadd_rn(cum.z, c.z)) : c;
       ++n_samples;
     }
-    if (a.S > 0) cum = ((T)1 / (T)(S2)) * cum;
-    store_pixel<T>(a, pix, cum);
-    if (a.out_hit) a.out_hit[pix] = a.hit_mode == RT_HIT_RAY_COUNT ? (int)cx.n_rays : last_hit;
+    if (a.S > 0) {  // imagetracer.py:99-101
+      const double inv = __ddiv_rn(1.0, (double)S2);
+      cum = mk3<double>(__dmul_rn(inv, cum.x), __dmul_rn(inv, cum.y), __dmul_rn(inv, cum.z));
+    }
+    store_pixel<double>(a, pm.at(p, col, row), cum);
+    if (a.out_hit) a.out_hit[pm.at(p, col, row)] = a.hit_mode == RT_HIT_RAY_COUNT ? (int)cx.n_rays : last_hit;
   }
   block_count_add(a.counters + CNT_CLOSEST, cx.n_rays);
   block_count_add(a.counters + CNT_SAMPLES, n_samples);

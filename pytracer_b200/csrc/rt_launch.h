@@ -14,8 +14,10 @@ struct RenderArgs {
   uint64_t aa_state, aa_inc, pt_state, pt_inc;
   const uint64_t* replay;  // device copy of rt_render_params.replay_states
   int32_t part_mode, part_rank, part_count, out_f64;
-  int32_t hit_mode, _pad;
+  int32_t hit_mode, rows_compact;  // rows_compact: RT_PART_ROWS stores the owned rows densely
   void* out_rgb;           // float or double [H][W][3]
+  float* peer_out[RT_MAX_PEERS];  // n_peers > 0: fp32 full-size images of all ranks, every pixel goes to each
+  int32_t n_peers, _pad2;
   int32_t* out_hit;        // optional
   unsigned long long* counters;
   JumpTable jump;          // for the jitter stream (aa_inc)
@@ -62,3 +64,4 @@ cudaError_t launch_tone_map(const float* d_rgb, long long n_pixels, int flags, d
                             unsigned char* d_out_ldr, int sm_count, cudaStream_t st);
 
 cudaError_t launch_ffma(float* out, int blocks, int iters, cudaStream_t st);
+cudaError_t launch_dfma(double* out, int blocks, int iters, cudaStream_t st);

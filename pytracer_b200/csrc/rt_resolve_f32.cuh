@@ -104,8 +104,8 @@ k_resolve_f32(const __grid_constant__ SceneView<float> sc, const __grid_constant
   // one sweep of all sphere pairs for one or two rays (block-uniform control flow)
   auto sweep = [&](bool two, bool on0, bool on1, const Ray<float>& r0, const Ray<float>& r1, int* c0, int& n0, int* c1, int& n1) {
     if (single) {
-      if (two) { if (on0 || on1) sweep_pairs2(buf[0], 0, 0, sc.n_pairs, r0, r1, c0, n0, c1, n1); }
-      else if (on0) sweep_pairs<true>(buf[0], 0, 0, sc.n_pairs, pack_ray(r0), c0, n0);
+      if (two) { if (on0 || on1) sweep_pairs2(buf[0], 0, 0, sc.n_pairs, r0, r1, sc.gate_a, sc.gate_t, c0, n0, c1, n1); }
+      else if (on0) sweep_pairs<true>(buf[0], 0, 0, sc.n_pairs, pack_ray(r0, sc.gate_a, sc.gate_t), c0, n0);
       return;
     }
     __syncthreads();  // the previous sweep is done with both buffers
@@ -118,8 +118,8 @@ k_resolve_f32(const __grid_constant__ SceneView<float> sc, const __grid_constant
       }
       mbar_wait(&bars[c & 1], parity[c & 1]);
       parity[c & 1] ^= 1u;
-      if (two) { if (on0 || on1) sweep_pairs2(buf[c & 1], b0, b0, b1, r0, r1, c0, n0, c1, n1); }
-      else if (on0) sweep_pairs<true>(buf[c & 1], b0, b0, b1, pack_ray(r0), c0, n0);
+      if (two) { if (on0 || on1) sweep_pairs2(buf[c & 1], b0, b0, b1, r0, r1, sc.gate_a, sc.gate_t, c0, n0, c1, n1); }
+      else if (on0) sweep_pairs<true>(buf[c & 1], b0, b0, b1, pack_ray(r0, sc.gate_a, sc.gate_t), c0, n0);
     }
   };
 
@@ -182,8 +182,8 @@ k_resolve_f32(const __grid_constant__ SceneView<float> sc, const __grid_constant
   }
   if (active) {
     if (a.S > 0) cum = (1.0f / (float)S2) * cum;  // imagetracer.py:99-101
-    store_pixel<float>(a, pix, cum);
-    if (a.out_hit) a.out_hit[pix] = a.hit_mode == RT_HIT_RAY_COUNT ? (int)(n_closest + n_shadow) : last_hit;
+    store_pixel<float>(a, pm.at(p, col, row), cum);
+    if (a.out_hit) a.out_hit[pm.at(p, col, row)] = a.hit_mode == RT_HIT_RAY_COUNT ? (int)(n_closest + n_shadow) : last_hit;
   }
   block_count_add(a.counters + CNT_CLOSEST, n_closest);
   block_count_add(a.counters + CNT_SHADOW, n_shadow);

@@ -312,8 +312,8 @@ k_resolve_hyb(const __grid_constant__ SceneView<double> sc, const __grid_constan
   }
   if (active) {
     if (a.S > 0) cum = (1.0 / (double)S2) * cum;  // imagetracer.py:99-101
-    store_pixel<double>(a, pix, cum);
-    if (a.out_hit) a.out_hit[pix] = a.hit_mode == RT_HIT_RAY_COUNT ? (int)(n_closest + n_shadow) : last_hit;
+    store_pixel<double>(a, pm.at(p, col, row), cum);
+    if (a.out_hit) a.out_hit[pm.at(p, col, row)] = a.hit_mode == RT_HIT_RAY_COUNT ? (int)(n_closest + n_shadow) : last_hit;
   }
   block_count_add(a.counters + CNT_CLOSEST, n_closest);
   block_count_add(a.counters + CNT_SHADOW, n_shadow);

@@ -308,7 +308,7 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
           if (count_rays) {
             if (MULTI_SLOT) atomicAdd(&slot_rays[slot], 1);
           } else if (primary_phase) {  // (warp-uniform)
-            if (last_of_pixel && a.out_hit) a.out_hit[pix] = found ? ss.orig[best] : -1;
+            if (last_of_pixel && a.out_hit) a.out_hit[pm.compact ? p0 + slot : pix] = found ? ss.orig[best] : -1;
           }
           if (!found) {
             contrib = mk3<float>(thr.x * cfg.bg[0], thr.y * cfg.bg[1], thr.z * cfg.bg[2]);
@@ -411,9 +411,9 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
       if (lane < G && p < pm.n_pixels) {
         int col, row;
         pm.locate(p, col, row);
-        store_pixel<float>(a, (long long)row * a.width + col,
+        store_pixel<float>(a, pm.at(p, col, row),
                            mk3<float>(acc[3 * lane] * inv_spp, acc[3 * lane + 1] * inv_spp, acc[3 * lane + 2] * inv_spp));
-        if (count_rays) a.out_hit[(long long)row * a.width + col] = slot_rays[lane];
+        if (count_rays) a.out_hit[pm.at(p, col, row)] = slot_rays[lane];
       }
       __syncwarp();
     } else if (ACC == ACC_LANES) {
@@ -430,8 +430,8 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
         if (lane == 0 && p < pm.n_pixels) {
           int col, row;
           pm.locate(p, col, row);
-          store_pixel<float>(a, (long long)row * a.width + col, mk3<float>(r * inv_spp, gr * inv_spp, b * inv_spp));
-          if (count_rays) a.out_hit[(long long)row * a.width + col] = slot_rays[g];
+          store_pixel<float>(a, pm.at(p, col, row), mk3<float>(r * inv_spp, gr * inv_spp, b * inv_spp));
+          if (count_rays) a.out_hit[pm.at(p, col, row)] = slot_rays[g];
         }
       }
       __syncwarp();
@@ -445,8 +445,8 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
       if (lane == 0 && p0 < pm.n_pixels) {
         int col, row;
         pm.locate(p0, col, row);
-        store_pixel<float>(a, (long long)row * a.width + col, mk3<float>(sr * inv_spp, sg * inv_spp, sb * inv_spp));
-        if (count_rays) a.out_hit[(long long)row * a.width + col] = (int)task_rays;
+        store_pixel<float>(a, pm.at(p0, col, row), mk3<float>(sr * inv_spp, sg * inv_spp, sb * inv_spp));
+        if (count_rays) a.out_hit[pm.at(p0, col, row)] = (int)task_rays;
       }
     }
   }

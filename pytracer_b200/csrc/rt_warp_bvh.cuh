@@ -113,7 +113,7 @@ k_pt_warp_bvh(const __grid_constant__ SceneView<float> sc, const __grid_constant
           thr = mk3<float>(1.f, 1.f, 1.f);
           depth = 0;
           origin = -1;
-          pix = (ls == L - 1) ? px : -1;
+          pix = (ls == L - 1) ? pm.at(p0 + slot, col, row) : -1;
           busy = true;
         }
         prim_next += take;
@@ -295,8 +295,8 @@ k_pt_warp_bvh(const __grid_constant__ SceneView<float> sc, const __grid_constant
       if (lane == 0 && p < pm.n_pixels) {
         int col, row;
         pm.locate(p, col, row);
-        store_pixel<float>(a, (long long)row * a.width + col, mk3<float>(r * inv_spp, gr * inv_spp, b * inv_spp));
-        if (count_rays) a.out_hit[(long long)row * a.width + col] = slot_rays[g];
+        store_pixel<float>(a, pm.at(p, col, row), mk3<float>(r * inv_spp, gr * inv_spp, b * inv_spp));
+        if (count_rays) a.out_hit[pm.at(p, col, row)] = slot_rays[g];
       }
     }
     __syncwarp();

@@ -170,3 +170,11 @@ def ffma_peak_tflops(iterations: int = 4096) -> Tuple[float, float]:
     tf, ms = C.c_double(0.0), C.c_float(0.0)
     _native.check(lib.rt_bench_ffma(iterations, C.byref(tf), C.byref(ms)))
     return tf.value, ms.value
+
+
+def dfma_peak_tflops(iterations: int = 1024) -> Tuple[float, float]:
+    """Measured FP64 FMA throughput of the current device: (TFLOP/s, kernel ms)."""
+    lib = _native.require_device()
+    tf, ms = C.c_double(0.0), C.c_float(0.0)
+    _native.check(lib.rt_bench_dfma(iterations, C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value

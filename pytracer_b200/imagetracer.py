@@ -12,8 +12,8 @@ and ``fire_all_rays(func, callback=None, callback_time_s=2.0, **callback_kwargs)
   ``func`` is applied to them in the reference's order on the host.
 
 Either way ``self.pcg`` is left where the reference leaves it: 2 draws per sample further.
-With a ``comm`` (see :mod:`pytracer_b200.dist`) every rank renders its share — strata of each pixel
-for path tracing, interleaved rows otherwise — and one NCCL sum yields the image on every rank.
+With a ``comm`` (see :mod:`pytracer_b200.dist`) every rank renders interleaved rows of the image and
+copies them into one page-locked host image shared by the ranks of the node, which ``image`` adopts.
 """
 from __future__ import annotations
 
@@ -67,9 +67,11 @@ class ImageTracer:
     def _fire_cuda(self, renderer: CudaRenderer, comm=None) -> None:
         scene = renderer.device_scene()
         if comm is not None and comm.world_size > 1:
-            from .dist import render_partitioned
+            # rows of the image interleaved over the ranks, each rank's rows copied straight into ONE
+            # page-locked host image shared by the node: the image object adopts that memory
+            from .dist import render_rows_to_shared_host
 
-            rgb, stats = render_partitioned(scene, self._params(renderer), comm, out=self._adoptable_buffer())
+            rgb, stats = render_rows_to_shared_host(scene, self._params(renderer), comm)
         else:
             rgb, _, stats = scene.render(self._params(renderer), out=self._adoptable_buffer())
         self.last_stats = renderer.last_stats = stats

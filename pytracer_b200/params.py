@@ -39,6 +39,7 @@ def make_params(
     out_f64: bool = False,
     hit_mode: int = _abi.RT_HIT_SHAPE,
     accel="none",
+    rows_layout: int = _abi.RT_ROWS_FULL,
 ) -> _abi.rt_render_params:
     p = _abi.rt_render_params()
     p.width, p.height, p.samples_per_side = int(width), int(height), int(samples_per_side)
@@ -60,4 +61,6 @@ def make_params(
     p.out_f64 = 1 if out_f64 else 0
     p.hit_mode = hit_mode
     p.accel = _abi.ACCELS[accel] if isinstance(accel, str) else int(accel)
+    p.rows_layout = int(rows_layout)
+    p.n_peer_images = 0
     return p

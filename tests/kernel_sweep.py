@@ -26,8 +26,9 @@ rs = scenes.random_spheres_scene(150, 3, 4, 10.0, with_light=True)
 big = DeviceScene(rs.world)
 for accel in ("none", "bvh"):
     for algo in ("flat", "pointlight"):
-        for prec in ("f32", "f64"):
-            run(big, rs.camera, 40, 24, algorithm=algo, samples_per_side=2, precision=prec, out_f64=(prec == "f64"), accel=accel)
+        for prec in ("f32", "f64") + (("hybrid",) if accel == "none" else ()):
+            for spp in (1, 2, 3):
+                run(big, rs.camera, 40, 24, algorithm=algo, samples_per_side=spp, precision=prec, out_f64=(prec != "f32"), accel=accel)
     for variant in ("warp", "mega"):
         run(big, rs.camera, 40, 24, algorithm="pathtracing", samples_per_side=2, num_of_rays=3, max_depth=3, variant=variant, accel=accel)
 # branching factors and depths at the edges of the work-stack sizing: N = 1 (a chain), deep trees, N larger
@@ -42,6 +43,14 @@ for n, depth, rr in ((1, 8, 3), (2, 6, 4), (40, 2, 2), (1100, 1, 3), (3, 0, 3)):
             got = lum(run(scene, camera, 32, 18, algorithm="pathtracing", samples_per_side=3, num_of_rays=n, max_depth=depth, rr_limit=rr,
                           variant="warp", accel=accel))
             assert abs(got - ref) <= 0.08 * ref + 1e-3, (n, depth, accel, got, ref)
+
+# max_depth < 0: every sample is BLACK without tracing a ray (render.py:100-101); a depth the wavefront
+# kernel's record format cannot hold (>= 1023): AUTO falls back to the depth-first kernel instead of failing
+for variant in ("auto", "warp", "mega"):
+    rgb, _, st = sc.render(make_params(16, 9, cam, algorithm="pathtracing", samples_per_side=2, num_of_rays=3, max_depth=-1, variant=variant))
+    assert not rgb.any() and st["rays_closest"] == 0 and st["samples"] == 16 * 9 * 4
+rgb, _, st = sc.render(make_params(16, 9, cam, algorithm="pathtracing", samples_per_side=1, num_of_rays=1, max_depth=2000, rr_limit=2))
+assert st["variant_used"] == _abi.RT_VARIANT_MEGA and np.isfinite(rgb).all()
 
 img = np.random.default_rng(1).random((37, 53, 3), dtype=np.float32) * 4
 tonemap.average_luminosity(img)

@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 
 from pytracer_b200 import _abi
 from pytracer_b200.dist import (TorchComm, choose_partition, partition_params, render_partitioned,
-                                rows_of_rank, strata_of_rank)
+                                render_rows_to_shared_host, rows_of_rank, rows_per_rank, strata_of_rank)
 from pytracer_b200.params import make_params
 from pytracer_b200.pcg import PCG
 from util import demo_flat
@@ -20,11 +20,18 @@ from util import demo_flat
 def test_partition_choice_and_coverage():
     PT, FLAT = _abi.RT_ALGO_PATHTRACING, _abi.RT_ALGO_FLAT
     assert choose_partition(PT, 8, 1) == _abi.RT_PART_NONE
-    assert choose_partition(PT, 8, 8) == _abi.RT_PART_SPP      # 64 spp over 8 GPUs: 8 strata each
-    assert choose_partition(PT, 4, 8) == _abi.RT_PART_SPP      # config 4: 16 spp, 2 strata each
-    assert choose_partition(PT, 2, 8) == _abi.RT_PART_ROWS     # 4 spp cannot be cut 8 ways
-    assert choose_partition(PT, 3, 2) == _abi.RT_PART_ROWS     # 9 strata do not split evenly in 2
-    assert choose_partition(FLAT, 8, 4) == _abi.RT_PART_ROWS   # deterministic renderers: rows
+    assert choose_partition(PT, 8, 8) == _abi.RT_PART_ROWS            # default: interleaved rows
+    assert choose_partition(PT, 8, 8, "spp") == _abi.RT_PART_SPP      # 64 spp over 8 GPUs: 8 strata each
+    assert choose_partition(PT, 4, 8, "spp") == _abi.RT_PART_SPP      # config 4: 16 spp, 2 strata each
+    assert choose_partition(PT, 2, 8, "spp") == _abi.RT_PART_ROWS     # 4 spp cannot be cut 8 ways
+    assert choose_partition(PT, 3, 2, "spp") == _abi.RT_PART_ROWS     # 9 strata do not split evenly in 2
+    assert choose_partition(FLAT, 8, 4, "spp") == _abi.RT_PART_ROWS   # deterministic renderers: rows
+    fs, cam = demo_flat()
+    p = partition_params(make_params(48, 36, cam, "flat", 2), 3, 8, "rows", _abi.RT_ROWS_COMPACT)
+    assert (p.part_mode, p.part_rank, p.part_count, p.rows_layout) == (_abi.RT_PART_ROWS, 3, 8, _abi.RT_ROWS_COMPACT)
+    p = partition_params(make_params(48, 36, cam, "pathtracing", 8), 3, 8, "spp", _abi.RT_ROWS_COMPACT)
+    assert (p.part_mode, p.rows_layout) == (_abi.RT_PART_SPP, _abi.RT_ROWS_FULL)
+    assert rows_per_rank(1080, 8) == 135 and rows_per_rank(37, 8) == 5
     for world in (2, 4, 8):
         strata = sorted(s for r in range(world) for s in strata_of_rank(8, r, world))
         assert strata == list(range(64))
@@ -68,6 +75,22 @@ def _worker(rank, world_size, port, out_dir):
     if rank == 0:
         np.save(os.path.join(out_dir, "image.npy"), image)
         np.save(os.path.join(out_dir, "stats.npy"), np.array([stats["rays_closest"], stats["rays_shadow"], stats["samples"]]))
+
+    # the shared host image: every rank copies only ITS rows into one POSIX shared-memory frame (what
+    # rt_render does with RT_ROWS_COMPACT), flag barriers in the same segment, counters summed through it
+    def oracle_rows_to_host(flat, p, out):
+        assert p.part_mode == _abi.RT_PART_ROWS and p.rows_layout == _abi.RT_ROWS_COMPACT and out.shape == (p.height, p.width, 3)
+        full, st = oracle_share(flat, p)
+        out[rank::world_size] = full.numpy()[rank::world_size]
+        return st
+
+    for frame in range(3):  # the segment is reused: the entry barrier keeps frames apart
+        shared_img, st2 = render_rows_to_shared_host(fs, params, comm, render_rows=oracle_rows_to_host, pin=False)
+        assert (st2["rays_closest"], st2["rays_shadow"], st2["samples"]) == (stats["rays_closest"], stats["rays_shadow"], stats["samples"])
+        assert np.array_equal(shared_img, image), (rank, frame)   # every rank sees the whole frame
+        comm.shared_image(params.height, params.width).barrier()  # everybody has compared
+        shared_img[rank::world_size] = -1.0  # scribble over the own rows: the next frame must overwrite them
+    comm.close()
     dist.barrier()
     dist.destroy_process_group()
 
