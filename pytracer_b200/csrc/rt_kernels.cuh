@@ -59,12 +59,19 @@ RT_DEV bool stratum_is_mine(const RenderArgs& a, int s) {
   return !(a.part_mode == RT_PART_SPP && a.part_count > 1) || (s % a.part_count) == a.part_rank;
 }
 
+// row split with the exchange folded into the kernel: the pixel goes to every rank's image.  Out of line:
+// the unrolled stores (24 per call site) would otherwise sit in the instruction stream of every render kernel
+static __device__ __noinline__ void store_pixel_peers(float* const* peer_out, int n_peers, long long off, float r, float g, float b) {
+#pragma unroll 1
+  for (int k = 0; k < n_peers; ++k) {
+    float* o = peer_out[k] + 3 * off;
+    o[0] = r; o[1] = g; o[2] = b;
+  }
+}
+
 template <typename T> RT_DEV void store_pixel(const RenderArgs& a, long long off, V3<T> c) {
-  if (a.n_peers > 0) {  // row split with the exchange folded into the kernel: the pixel goes to every rank's image
-    for (int k = 0; k < a.n_peers; ++k) {
-      float* o = a.peer_out[k] + 3 * off;
-      o[0] = (float)c.x; o[1] = (float)c.y; o[2] = (float)c.z;
-    }
+  if (a.n_peers > 0) {
+    store_pixel_peers(a.peer_out, a.n_peers, off, (float)c.x, (float)c.y, (float)c.z);
   } else if (a.out_f64) {
     double* o = (double*)a.out_rgb + 3 * off;
     o[0] = (double)c.x; o[1] = (double)c.y; o[2] = (double)c.z;

@@ -203,14 +203,20 @@ def read_pfm_image(stream) -> HdrImage:
     return HdrImage.from_array(data[::-1].astype(np.float32))
 
 
-def install_array(image, rgb: np.ndarray) -> None:
-    """Put a rendered (H, W, 3) array into any HdrImage-like object.  Our own class adopts the array;
-    a reference ``pytracer.hdrimages.HdrImage`` gets a :class:`PixelView` as its ``pixels`` (built
-    on the reference's own ``Color`` type) — no per-pixel Python work in either case."""
+def install_array(image, rgb: np.ndarray, adopt: bool = False) -> None:
+    """Put a rendered (H, W, 3) array into any HdrImage-like object.  Our own class adopts the array
+    (``adopt=True``: always, without a copy — the node's shared page-locked image of a multi-GPU render,
+    whose owner keeps it alive and registered); a reference ``pytracer.hdrimages.HdrImage`` gets a
+    :class:`PixelView` as its ``pixels`` (built on the reference's own ``Color`` type) — no per-pixel
+    Python work in either case."""
     if isinstance(image, HdrImage):
         if rgb is image._rgb:  # rendered straight into the image's own (page-locked) buffer
             return
-        if image._rgb.shape == rgb.shape and image._rgb.dtype == rgb.dtype:
+        if adopt and rgb.dtype == image._rgb.dtype and rgb.flags.c_contiguous:
+            image.unpin()
+            image._rgb = rgb
+            image.height, image.width = int(rgb.shape[0]), int(rgb.shape[1])
+        elif image._rgb.shape == rgb.shape and image._rgb.dtype == rgb.dtype:
             np.copyto(image._rgb, rgb)
         else:
             image.unpin()  # never leave a registration on a buffer numpy is about to free

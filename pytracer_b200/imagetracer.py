@@ -66,7 +66,8 @@ class ImageTracer:
     # -- the product path
     def _fire_cuda(self, renderer: CudaRenderer, comm=None) -> None:
         scene = renderer.device_scene()
-        if comm is not None and comm.world_size > 1:
+        shared = comm is not None and comm.world_size > 1
+        if shared:
             # rows of the image interleaved over the ranks, each rank's rows copied straight into ONE
             # page-locked host image shared by the node: the image object adopts that memory
             from .dist import render_rows_to_shared_host
@@ -77,7 +78,7 @@ class ImageTracer:
         self.last_stats = renderer.last_stats = stats
         if renderer.algorithm == "pathtracing":
             renderer.pcg.random()  # the next image must not reuse these sample streams
-        install_array(self.image, rgb)
+        install_array(self.image, rgb, adopt=shared)  # the shared image is adopted, never copied (24.9 MB per frame)
 
     def _adoptable_buffer(self) -> Optional[np.ndarray]:
         arr = getattr(self.image, "_rgb", None)

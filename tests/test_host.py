@@ -338,3 +338,20 @@ def test_flat_scene_knows_when_only_transformations_changed():
     w, _ = scenes.demo_scene(clock=10.0)
     w.shapes[2].transformation = translation(Vec(0.0, 0.0, 2.0))
     assert a.differs_only_in_transforms(flatten_world(w))
+
+
+def test_install_array_adopts_a_shared_frame_without_copying():
+    """Multi-GPU frames land in the node's shared page-locked image; the HdrImage must take that memory
+    over as it is (a 24.9 MB copy per frame was the host tail of the 8-GPU end-to-end number)."""
+    from pytracer_b200.hdrimage import HdrImage, install_array
+
+    img = HdrImage(8, 4)
+    own = img.rgb_array()
+    frame = np.arange(4 * 8 * 3, dtype=np.float32).reshape(4, 8, 3)
+    install_array(img, frame)                      # default: the caller's buffer is kept, values copied
+    assert img.rgb_array() is own and np.array_equal(own, frame)
+    shared = frame * 2
+    install_array(img, shared, adopt=True)         # shared frame: adopted
+    assert img.rgb_array() is shared and img.get_pixel(1, 0).r == shared[0, 1, 0]
+    install_array(img, shared, adopt=True)         # next frame into the same memory: nothing to do
+    assert img.rgb_array() is shared
