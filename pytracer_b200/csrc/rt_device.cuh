@@ -180,10 +180,18 @@ RT_DEV bool scan_any(const T* __restrict__ xf, int begin, int end, int n_spheres
 // is rounding noise (phantom hits on spheres the ray passes at a distance), while |q|^2 is formed from a
 // vector of the size of the answer.  The sweep keeps the cheap discriminant as its gate; every decision
 // about a sphere (closest hit, shadow test, hierarchy leaf) comes from here.
-RT_DEV bool sphere_cross(const float* __restrict__ im, const Ray<float>& r, float& tm, float& half) {
-  const float4 r0 = reinterpret_cast<const float4*>(im)[0];
-  const float4 r1 = reinterpret_cast<const float4*>(im)[1];
-  const float4 r2 = reinterpret_cast<const float4*>(im)[2];
+struct Rows3 {  // a 3x4 transform as three rows already in registers
+  float4 r0, r1, r2;
+};
+RT_DEV Rows3 rows_at(const float* __restrict__ p) {
+  Rows3 M;
+  M.r0 = reinterpret_cast<const float4*>(p)[0];
+  M.r1 = reinterpret_cast<const float4*>(p)[1];
+  M.r2 = reinterpret_cast<const float4*>(p)[2];
+  return M;
+}
+RT_DEV bool sphere_cross_rows(const Rows3& M, const Ray<float>& r, float& tm, float& half) {
+  const float4 r0 = M.r0, r1 = M.r1, r2 = M.r2;
   const float px = fmaf(r0.x, r.o.x, fmaf(r0.y, r.o.y, fmaf(r0.z, r.o.z, r0.w)));
   const float py = fmaf(r1.x, r.o.x, fmaf(r1.y, r.o.y, fmaf(r1.z, r.o.z, r1.w)));
   const float pz = fmaf(r2.x, r.o.x, fmaf(r2.y, r.o.y, fmaf(r2.z, r.o.z, r2.w)));
@@ -199,6 +207,9 @@ RT_DEV bool sphere_cross(const float* __restrict__ im, const Ray<float>& r, floa
   tm = -s;
   half = fast_sqrt(fmaxf(w, 0.0f));
   return w > 0.0f;  // false for a = 0 too (s is NaN): the reference's delta = b^2 = 0 is a miss as well
+}
+RT_DEV bool sphere_cross(const float* __restrict__ im, const Ray<float>& r, float& tm, float& half) {
+  return sphere_cross_rows(rows_at(im), r, tm, half);
 }
 
 #define RT_CAND_CAP 16
@@ -502,42 +513,6 @@ RT_DEV void closest_all_warp(const SceneView<float>& sc, const ScanSrc<float>& s
   }
 }
 
-// Scenes of a handful of shapes (demo.txt: one sphere, two planes): no sweep / candidate list, every
-// shape is tested directly from the plain [n][12] table (held in shared memory by the caller), and the
-// tests are written without branches: with 32 different rays per warp some lane crosses every shape
-// anyway, so a branch only adds its own overhead.  Same decisions as sphere_t_at / plane_t.
-RT_DEV float sphere_t_few(const float* __restrict__ im, const Ray<float>& r, bool is_origin) {
-  float tm, half;
-  bool ok = sphere_cross(im, r, tm, half);
-  const float t1 = tm - half, t2 = tm + half;
-  float t = (t1 > r.tmin && t1 < r.tmax) ? t1 : t2;  // the first root inside (tmin, tmax), shapes.py:112-119
-  if (is_origin) { t = 2.0f * tm; ok = true; }  // see sphere_t_at
-  return (ok && t > r.tmin && t < r.tmax) ? t : Num<float>::inf();
-}
-RT_DEV float plane_t_few(const float* __restrict__ im, const Ray<float>& r, bool is_origin) {
-  const float4 row = reinterpret_cast<const float4*>(im)[2];
-  const float oz = fmaf(r.o.x, row.x, fmaf(r.o.y, row.y, fmaf(r.o.z, row.z, row.w)));
-  const float dz = fmaf(r.d.x, row.x, fmaf(r.d.y, row.y, r.d.z * row.z));
-  const float t = -oz * fast_rcp(dz);
-  const bool ok = !(fabsf(dz) < 1e-5f) && t > r.tmin && t < r.tmax && !is_origin;
-  return ok ? t : Num<float>::inf();
-}
-RT_DEV void closest_few(const SceneView<float>& sc, const Ray<float>& r, float& best_t, int& best, int origin) {
-#pragma unroll 1
-  for (int i = 0; i < sc.n_spheres; ++i) {
-    const float t = sphere_t_few(sc.invm + 12 * i, r, i == origin);
-    if (t < best_t) { best_t = t; best = i; }
-  }
-#pragma unroll 1
-  for (int i = sc.n_spheres; i < sc.n_shapes; ++i) {
-    const float t = plane_t_few(sc.invm + 12 * i, r, i == origin);
-    if (t < best_t) { best_t = t; best = i; }
-    else if (t == best_t && best >= 0 && best < sc.n_spheres) {  // world.py:62 on a sphere / plane tie
-      if (plane_wins_tie(sc.orig, i, best)) { best_t = t; best = i; }
-    }
-  }
-}
-
 template <bool UNROLL2>
 RT_DEV void closest_all_f32(const SceneView<float>& sc, const ScanSrc<float>& src, const Ray<float>& r,
                             float& best_t, int& best, int origin = -1) {
@@ -585,6 +560,30 @@ template <typename T> RT_DEV LocalHit<T> local_hit(const T* im, const Ray<T>& r,
   L.d = xf_vec(im, r.d);
   L.hp = o + t * L.d;
   return L;
+}
+// the same two steps for the fp32 wavefront kernel, on transform rows already in registers
+RT_DEV LocalHit<float> local_hit_rows(const Rows3& M, const Ray<float>& r, float t) {
+  LocalHit<float> L;
+  const V3<float> o = mk3<float>(fmaf(r.o.x, M.r0.x, fmaf(r.o.y, M.r0.y, fmaf(r.o.z, M.r0.z, M.r0.w))),
+                                 fmaf(r.o.x, M.r1.x, fmaf(r.o.y, M.r1.y, fmaf(r.o.z, M.r1.z, M.r1.w))),
+                                 fmaf(r.o.x, M.r2.x, fmaf(r.o.y, M.r2.y, fmaf(r.o.z, M.r2.z, M.r2.w))));
+  L.d = mk3<float>(fmaf(r.d.x, M.r0.x, fmaf(r.d.y, M.r0.y, r.d.z * M.r0.z)),
+                   fmaf(r.d.x, M.r1.x, fmaf(r.d.y, M.r1.y, r.d.z * M.r1.z)),
+                   fmaf(r.d.x, M.r2.x, fmaf(r.d.y, M.r2.y, r.d.z * M.r2.z)));
+  L.hp = o + t * L.d;
+  return L;
+}
+RT_DEV void world_frame_rows(const Rows3& I, const Rows3& M, const LocalHit<float>& L, bool sphere, V3<float>& point, V3<float>& normal) {
+  point = mk3<float>(fmaf(L.hp.x, M.r0.x, fmaf(L.hp.y, M.r0.y, fmaf(L.hp.z, M.r0.z, M.r0.w))),
+                     fmaf(L.hp.x, M.r1.x, fmaf(L.hp.y, M.r1.y, fmaf(L.hp.z, M.r1.z, M.r1.w))),
+                     fmaf(L.hp.x, M.r2.x, fmaf(L.hp.y, M.r2.y, fmaf(L.hp.z, M.r2.z, M.r2.w))));
+  V3<float> n;
+  if (sphere) n = (dot(L.hp, L.d) < 0.f) ? L.hp : -L.hp;  // shapes.py:45-54
+  else n = mk3<float>(0.f, 0.f, (L.d.z < 0.f) ? 1.f : -1.f);
+  n = mk3<float>(fmaf(n.x, I.r0.x, fmaf(n.y, I.r1.x, n.z * I.r2.x)),   // transpose of the inverse
+                 fmaf(n.x, I.r0.y, fmaf(n.y, I.r1.y, n.z * I.r2.y)),
+                 fmaf(n.x, I.r0.z, fmaf(n.y, I.r1.z, n.z * I.r2.z)));
+  normal = normalize(n);
 }
 template <typename T> RT_DEV void local_uv(const LocalHit<T>& L, bool sphere, T& u_out, T& v_out) {
   if (sphere) {

@@ -46,8 +46,13 @@ struct WarpCfg {
   unsigned long long n_samples;  // samples this launch traces (all tasks), added to the counter once
 };
 
-// SMALL instantiation: every table of the scene lives in shared memory at FIXED offsets (capacity
-// for the largest small scene, 5.6 KB), so that table addresses are immediates in the per-ray code.
+// SMALL instantiation: every table of the scene lives in shared memory at FIXED offsets (capacity for
+// the largest small scene, 3.3 KB), re-packed by the staging loop into what the per-ray code reads:
+//   SM_INVM / SM_M   [16][12] fp32 transforms (three LDS.128 per shape)
+//   SM_ORIG          [16] index in World.shapes
+//   SM_SHAPE_MAT     [16] the shape's material as one int4 {brdf_kind, brdf_pigment, emitted_pigment, flags}
+//                    (no material-index indirection)
+//   SM_PIG           [32] 48-byte pigment records {kind, steps, tex_w, tex_h | c1.xyz, c2.x | c2.yz, texture handle}
 #define RT_SMALL_MAX_SPHERES 8
 #define RT_SMALL_MAX_SHAPES 16
 #define RT_SMALL_MAX_MATERIALS 16
@@ -56,10 +61,10 @@ enum {
   SM_INVM = 0,
   SM_M = SM_INVM + RT_SMALL_MAX_SHAPES * 48,
   SM_ORIG = SM_M + RT_SMALL_MAX_SHAPES * 48,
-  SM_MATERIAL = SM_ORIG + RT_SMALL_MAX_SHAPES * 4,
-  SM_MATERIALS = SM_MATERIAL + RT_SMALL_MAX_SHAPES * 4,
-  SM_PIGMENTS = (SM_MATERIALS + RT_SMALL_MAX_MATERIALS * (int)sizeof(DevMaterial) + 15) / 16 * 16,
-  SM_BYTES = (SM_PIGMENTS + RT_SMALL_MAX_PIGMENTS * (int)sizeof(DevPigment) + 15) / 16 * 16
+  SM_SHAPE_MAT = SM_ORIG + RT_SMALL_MAX_SHAPES * 4,
+  SM_PIG = SM_SHAPE_MAT + RT_SMALL_MAX_SHAPES * 16,
+  SM_PIG_STRIDE = 48,
+  SM_BYTES = SM_PIG + RT_SMALL_MAX_PIGMENTS * SM_PIG_STRIDE
 };
 #ifndef RT_SMALL_THREADS
 #define RT_SMALL_THREADS 256
@@ -72,6 +77,94 @@ RT_DEV void stage_words(void* sh, const void* g, int bytes) {  // 4-byte granula
   const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
   uint32_t* dst = reinterpret_cast<uint32_t*>(sh);
   for (int i = threadIdx.x; i < bytes / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// ---- shared memory by 32-bit window address ------------------------------------------------------
+// On sm_100 the address an LDS takes is (cluster CTA id << 24) + offset, and the compiler re-derives
+// that base (S2R SR_CgaCtaId + LEA, ~25 cycles of latency each time) at nearly every access when
+// registers are short: ncu counted 11 such sequences per iteration of the drain loop on demo.txt, 6 %
+// of the instruction stream.  The wavefront kernel therefore keeps ONE base address per warp that has
+// been passed through a shuffle (not re-derivable) and addresses its work stack and the staged scene
+// tables relative to it with explicit ld.shared / st.shared.
+RT_DEV float4 lds4(uint32_t a) {  // read/write data (work stack): ordered against st.shared and __syncwarp
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+RT_DEV void sts4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+RT_DEV float4 lds4c(uint32_t a) {  // tables that are constant once staged: free to schedule and to merge
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+RT_DEV int4 lds4ic(uint32_t a) {
+  int4 v;
+  asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+RT_DEV int ldsic(uint32_t a) {
+  int v;
+  asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+RT_DEV Rows3 lds_rows(uint32_t a) {
+  Rows3 m;
+  m.r0 = lds4c(a); m.r1 = lds4c(a + 16); m.r2 = lds4c(a + 32);
+  return m;
+}
+
+// Closest hit over a handful of shapes staged at `sb` (demo.txt: one sphere, two planes): World.ray_intersection
+// (world.py:51-69) without a sweep / candidate list, every shape tested directly and without branches —
+// with 32 different rays per warp some lane crosses every shape anyway.  Rays of the path tracer are
+// unbounded (tmax = inf, ray.py:31), so only tmin is tested.  Spheres and planes keep separate minima
+// (strict '<': the first of each kind wins a tie like world.py:62) and the rare sphere-vs-plane tie is
+// resolved once at the end on the index in World.shapes.
+RT_DEV void closest_small(uint32_t sb, int n_spheres, int n_shapes, const Ray<float>& r, int origin, float& best_t, int& best) {
+  const float inf = Num<float>::inf();
+  float ts = inf, tp = inf;
+  int is = -1, ip = -1;
+  uint32_t a = sb + SM_INVM;
+#pragma unroll 1
+  for (int i = 0; i < n_spheres; ++i, a += 48) {
+    float tm, half;
+    bool ok = sphere_cross_rows(lds_rows(a), r, tm, half);
+    const float t1 = tm - half;
+    float t = (t1 > r.tmin) ? t1 : tm + half;   // the first root beyond tmin, shapes.py:112-119
+    if (i == origin) { t = 2.0f * tm; ok = true; }  // see sphere_t_at
+    if (ok && t > r.tmin && t < ts) { ts = t; is = i; }
+  }
+#pragma unroll 1
+  for (int i = n_spheres; i < n_shapes; ++i, a += 48) {
+    const float4 row = lds4c(a + 32);
+    const float oz = fmaf(r.o.x, row.x, fmaf(r.o.y, row.y, fmaf(r.o.z, row.z, row.w)));
+    const float dz = fmaf(r.d.x, row.x, fmaf(r.d.y, row.y, r.d.z * row.z));
+    const float t = -oz * fast_rcp(dz);
+    if (!(fabsf(dz) < 1e-5f) && t > r.tmin && t < tp && i != origin) { tp = t; ip = i; }
+  }
+  bool plane = tp < ts;
+  if (tp == ts && ip >= 0 && is >= 0) plane = ldsic(sb + SM_ORIG + 4 * ip) < ldsic(sb + SM_ORIG + 4 * is);
+  best_t = plane ? tp : ts;
+  best = plane ? ip : is;
+}
+
+// Pigment.get_color (materials.py:58, :70-82, :96-100) from a staged 48-byte record
+RT_DEV V3<float> pigment_color_small(uint32_t pa, float u, float v) {
+  const int4 h = lds4ic(pa);
+  const float4 q = lds4c(pa + 16);
+  if (h.x == RT_PIGMENT_UNIFORM) return mk3<float>(q.x, q.y, q.z);
+  const float4 w = lds4c(pa + 32);
+  if (h.x == RT_PIGMENT_CHECKERED) {
+    const int iu = __float2int_rd(u * (float)h.y), iv = __float2int_rd(v * (float)h.y);
+    return (((iu ^ iv) & 1) == 0) ? mk3<float>(q.x, q.y, q.z) : mk3<float>(q.w, w.x, w.y);
+  }
+  int col = (int)(u * (float)h.z), row = (int)(v * (float)h.w);
+  col = min(max(col, 0), h.z - 1);
+  row = min(max(row, 0), h.w - 1);
+  const cudaTextureObject_t tex = ((unsigned long long)__float_as_uint(w.w) << 32) | (unsigned long long)__float_as_uint(w.z);
+  const float4 t = fetch_texel(tex, col + 0.5f, row + 0.5f);
+  return mk3<float>(t.x, t.y, t.z);
 }
 
 // Primary ray of the path tracer's warp kernels.  Same formulas as primary_ray<T> (imagetracer.py:48-58,
@@ -125,34 +218,42 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
           const __grid_constant__ WarpCfg cfg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5;
   ScanSrc<float> src = global_src<float>(sc);
-  SceneView<float> ss = sc;  // the view the per-ray code reads: shared-memory copies for SMALL
   if (SMALL) {
     stage_words(smem_raw + SM_INVM, sc.invm, sc.n_shapes * 48);
     stage_words(smem_raw + SM_M, sc.m, sc.n_shapes * 48);
     stage_words(smem_raw + SM_ORIG, sc.orig, sc.n_shapes * 4);
-    stage_words(smem_raw + SM_MATERIAL, sc.material, sc.n_shapes * 4);
-    stage_words(smem_raw + SM_MATERIALS, sc.materials, sc.n_materials * (int)sizeof(DevMaterial));
-    stage_words(smem_raw + SM_PIGMENTS, sc.pigments, sc.n_pigments * (int)sizeof(DevPigment));
+    for (int i = threadIdx.x; i < sc.n_shapes; i += blockDim.x) {
+      const DevMaterial& mt = sc.materials[sc.material[i]];
+      reinterpret_cast<int4*>(smem_raw + SM_SHAPE_MAT)[i] = make_int4(mt.brdf_kind, mt.brdf_pigment, mt.emitted_pigment, mt.flags);
+    }
+    for (int i = threadIdx.x; i < sc.n_pigments; i += blockDim.x) {
+      const DevPigment& pg = sc.pigments[i];
+      float4* o = reinterpret_cast<float4*>(smem_raw + SM_PIG + i * SM_PIG_STRIDE);
+      o[0] = make_float4(__int_as_float(pg.kind), __int_as_float(pg.steps), __int_as_float(pg.tex_w), __int_as_float(pg.tex_h));
+      o[1] = make_float4(pg.c1[0], pg.c1[1], pg.c1[2], pg.c2[0]);
+      o[2] = make_float4(pg.c2[1], pg.c2[2], __uint_as_float((uint32_t)pg.tex), __uint_as_float((uint32_t)((unsigned long long)pg.tex >> 32)));
+    }
     __syncthreads();
-    ss.invm = reinterpret_cast<const float*>(smem_raw + SM_INVM);
-    ss.m = reinterpret_cast<const float*>(smem_raw + SM_M);
-    ss.orig = reinterpret_cast<const int32_t*>(smem_raw + SM_ORIG);
-    ss.material = reinterpret_cast<const int32_t*>(smem_raw + SM_MATERIAL);
-    ss.materials = reinterpret_cast<const DevMaterial*>(smem_raw + SM_MATERIALS);
-    ss.pigments = reinterpret_cast<const DevPigment*>(smem_raw + SM_PIGMENTS);
   } else if (SHAPES_SMEM) {
     stage_bytes(smem_raw, sc.packed, (size_t)sc.n_pairs * 96 + (size_t)(sc.n_shapes - sc.n_spheres) * 48);
     __syncthreads();
     src.pairs = reinterpret_cast<const float4*>(smem_raw);
     src.planes = reinterpret_cast<const float*>(smem_raw) + 24 * (size_t)sc.n_pairs;
   }
-  unsigned char* wbase = smem_raw + (SMALL ? (int)SM_BYTES : cfg.shape_bytes) + warp * cfg.per_warp_bytes;
-  ScatterRec* stack = reinterpret_cast<ScatterRec*>(wbase);
-  ScatterRec* cur = stack + cfg.cap;
+  // lane index and the two shared-window addresses the loop lives on, each passed through a shuffle so
+  // that they are values held (or spilled) instead of special-register sequences re-derived at every use
+  const int lane0 = threadIdx.x & 31;
+  const int lane = __shfl_sync(FULL, lane0, lane0);
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  // (lane 0's value of a lane-dependent expression: a shuffle of a warp-uniform value would be folded away)
+  const uint32_t sb = __shfl_sync(FULL, smem0 + (uint32_t)lane0, 0);  // staged scene tables (SMALL)
+  const int wofs = (SMALL ? (int)SM_BYTES : cfg.shape_bytes) + warp * cfg.per_warp_bytes;
+  const uint32_t wb = __shfl_sync(FULL, smem0 + (uint32_t)(wofs + lane0), 0);  // this warp's record stack
+  const uint32_t curb = wb + (uint32_t)cfg.cap * (uint32_t)sizeof(ScatterRec);  // the partly consumed record
   constexpr bool MULTI_SLOT = ACC != ACC_REG;
-  int* slot_rays = reinterpret_cast<int*>(cur + 1);        // [32], multi-pixel tasks + RT_HIT_RAY_COUNT
+  int* slot_rays = reinterpret_cast<int*>(smem_raw + wofs + (size_t)(cfg.cap + 1) * sizeof(ScatterRec));  // [32], multi-pixel tasks + RT_HIT_RAY_COUNT
   float* acc = reinterpret_cast<float*>(slot_rays + 32);   // ACC_SEG: [32][3]; ACC_LANES: [G][3][32]
   const bool count_rays = a.out_hit != nullptr && a.hit_mode == RT_HIT_RAY_COUNT;
 
@@ -163,7 +264,7 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
   // x / N for 0 <= x <= 32 as a multiply-shift (exact for N <= 1024; beyond that x / N is 0 or 1)
   auto div_n = [&](int x) -> int { return cfg.n_magic ? (int)(((unsigned)x * cfg.n_magic) >> 16) : (x >= N ? 1 : 0); };
   const float inv_n = cfg.inv_n, inv_spp = cfg.inv_spp;
-  // rays are counted once per iteration from warp-uniform quantities (every lane holds the same sum)
+  // rays are counted per task from warp-uniform quantities (every lane holds the same sum)
   unsigned int n_rays = 0;
   bool overflow = false;
 
@@ -180,8 +281,8 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
       pm.locate(p0, col, row);
       aa_task = pcg_jump(a.aa_state, 2ull * (unsigned long long)((long long)row * a.width + col) * S2, a.jump);
     }
-    float sr = 0.f, sg = 0.f, sb = 0.f;  // lane-private sums (single-slot tasks)
-    unsigned int task_rays = 0;          // warp-uniform
+    float sr = 0.f, sg = 0.f, sb_ = 0.f;  // lane-private sums (single-slot tasks)
+    unsigned int task_rays = 0;           // warp-uniform
     const int task_prims = (int)min((long long)G, pm.n_pixels - p0) * L;  // primaries of this task
     if (MULTI_SLOT) {
       if (ACC == ACC_SEG) { for (int i = lane; i < 96; i += 32) acc[i] = 0.f; }
@@ -212,9 +313,7 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
           const int ls = j - slot * L;
           const long long p = p0 + slot;
           active = (j < G * L) && (p < pm.n_pixels);
-          const unsigned n_act = (unsigned)min(max(task_prims - round * 32, 0), 32);
-          n_rays += n_act;
-          task_rays += n_act;
+          task_rays += (unsigned)min(max(task_prims - round * 32, 0), 32);
           if (active) {
             int col, row;
             pm.locate(p, col, row);
@@ -235,22 +334,18 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
           if (avail == 0) break;
           const int take = (int)min(avail, 32ll);
           active = lane < take;
-          n_rays += (unsigned)take;
           task_rays += (unsigned)take;
+          // the first `from_cur` lanes finish the partly consumed record, the others take whole records
+          // off the top, N lanes each: one address per lane, one set of three broadcast LDS.128
           const int from_cur = min(cur_rem, take);
+          const int jj = max(lane - from_cur, 0);
+          const int r = div_n(jj);
+          const bool on_cur = lane < from_cur;
+          const int child = on_cur ? cur_done + lane : jj - r * N;
+          if (ACC == ACC_SEG) seg_start = on_cur ? 0 : from_cur + r * N;
+          const uint32_t ra = (on_cur || !active) ? curb : wb + (uint32_t)(top - 1 - r) * (uint32_t)sizeof(ScatterRec);
           ScatterRec rec;
-          int child = 0;
-          if (lane < from_cur) {
-            rec = *cur;
-            child = cur_done + lane;
-            seg_start = 0;
-          } else if (active) {
-            const int jj = lane - from_cur;
-            const int r = div_n(jj);
-            child = jj - r * N;
-            rec = stack[top - 1 - r];
-            seg_start = from_cur + r * N;
-          }
+          rec.a = lds4(ra); rec.b = lds4(ra + 16); rec.c = lds4(ra + 32);
           // bookkeeping, identical in all lanes
           const int rest = take - from_cur;
           const int full = div_n(rest), part = rest - full * N;
@@ -259,8 +354,8 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
           __syncwarp();  // every lane has read its record
           int new_top = top - full;
           if (part > 0) {  // the next record is only partly consumed: it becomes `cur`
-            if (lane < 3) reinterpret_cast<float4*>(cur)[lane] = reinterpret_cast<const float4*>(&stack[new_top - 1])[lane];
             new_top -= 1;
+            if (lane < 3) sts4(curb + 16 * lane, lds4(wb + (uint32_t)new_top * (uint32_t)sizeof(ScatterRec) + 16 * lane));
             cur_rem = N - part;
             cur_done = part;
           }
@@ -302,13 +397,14 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
           closest_all_warp(sc, src, ray, active, best_t, best, origin);
         }
         if (active) {
-          if (SMALL) closest_few(ss, ray, best_t, best, origin);
+          if (SMALL) closest_small(sb, sc.n_spheres, sc.n_shapes, ray, origin, best_t, best);
           else if (!RT_WARP_SPLIT) closest_all_f32<true>(sc, src, ray, best_t, best, origin);
           const bool found = best >= 0;
           if (count_rays) {
             if (MULTI_SLOT) atomicAdd(&slot_rays[slot], 1);
           } else if (primary_phase) {  // (warp-uniform)
-            if (last_of_pixel && a.out_hit) a.out_hit[pm.compact ? p0 + slot : pix] = found ? ss.orig[best] : -1;
+            if (last_of_pixel && a.out_hit)
+              a.out_hit[pm.compact ? p0 + slot : pix] = !found ? -1 : (SMALL ? ldsic(sb + SM_ORIG + 4 * best) : sc.orig[best]);
           }
           if (!found) {
             contrib = mk3<float>(thr.x * cfg.bg[0], thr.y * cfg.bg[1], thr.z * cfg.bg[2]);
@@ -316,30 +412,45 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
             // The hit record is built lazily (rt_device.cuh local_hit / local_uv / world_frame): most rays
             // of a tree are its leaves, whose children render.py:100-101 cuts — for those only the emitted
             // colour matters, which for a uniform pigment needs no record at all.
-            const DevMaterial& mat = ss.materials[ss.material[best]];
-            const int mf = mat.flags;
-            const bool sphere = best < ss.n_spheres;
-            const float* im = ss.invm + 12 * best;
+            int brdf_kind, brdf_pig, emit_pig, mf;
+            Rows3 im;
+            const bool sphere = best < sc.n_spheres;
+            if (SMALL) {
+              const int4 mt = lds4ic(sb + SM_SHAPE_MAT + 16 * best);
+              brdf_kind = mt.x; brdf_pig = mt.y; emit_pig = mt.z; mf = mt.w;
+            } else {
+              const DevMaterial& mat = sc.materials[sc.material[best]];
+              brdf_kind = mat.brdf_kind; brdf_pig = mat.brdf_pigment; emit_pig = mat.emitted_pigment; mf = mat.flags;
+            }
+            auto rows_of = [&](bool inverse) -> Rows3 {
+              if (SMALL) return lds_rows(sb + (inverse ? SM_INVM : SM_M) + 48 * best);
+              return rows_at((inverse ? sc.invm : sc.m) + 12 * (size_t)best);
+            };
+            auto pig_uniform = [&](int idx) -> V3<float> {
+              if (SMALL) { const float4 q = lds4c(sb + SM_PIG + idx * SM_PIG_STRIDE + 16); return mk3<float>(q.x, q.y, q.z); }
+              return pig_c1<float>(sc.pigments[idx]);
+            };
+            auto pig_at = [&](int idx, float u, float v) -> V3<float> {
+              if (SMALL) return pigment_color_small(sb + SM_PIG + idx * SM_PIG_STRIDE, u, v);
+              return pigment_color<float>(sc.pigments, idx, u, v);
+            };
             float u = 0.f, v = 0.f;
             if (depth >= a.max_depth) {
               // every child would come back BLACK, so neither the roulette draw (render.py:116-123) nor
               // the BRDF colour can change the result: emitted radiance only
               if (!(mf & MAT_EMIT_BLACK)) {
-                if (mf & MAT_UV_EMIT) local_uv<float>(local_hit<float>(im, ray, best_t), sphere, u, v);
-                contrib = mul3(thr, (mf & MAT_UV_EMIT) ? pigment_color<float>(ss.pigments, mat.emitted_pigment, u, v)
-                                                       : pig_c1<float>(ss.pigments[mat.emitted_pigment]));
+                if (mf & MAT_UV_EMIT) local_uv<float>(local_hit_rows(rows_of(true), ray, best_t), sphere, u, v);
+                contrib = mul3(thr, (mf & MAT_UV_EMIT) ? pig_at(emit_pig, u, v) : pig_uniform(emit_pig));
               }
             } else {
               const bool scatters = !(mf & MAT_NO_SCATTER);
               LocalHit<float> lh;
-              if (scatters || (mf & MAT_USES_UV)) lh = local_hit<float>(im, ray, best_t);
+              if (scatters || (mf & MAT_USES_UV)) { im = rows_of(true); lh = local_hit_rows(im, ray, best_t); }
               if (mf & MAT_USES_UV) local_uv<float>(lh, sphere, u, v);
               if (!(mf & MAT_EMIT_BLACK))
-                contrib = mul3(thr, (mf & MAT_UV_EMIT) ? pigment_color<float>(ss.pigments, mat.emitted_pigment, u, v)
-                                                       : pig_c1<float>(ss.pigments[mat.emitted_pigment]));
+                contrib = mul3(thr, (mf & MAT_UV_EMIT) ? pig_at(emit_pig, u, v) : pig_uniform(emit_pig));
               if (scatters) {
-                V3<float> hit_color = (mf & MAT_UV_BRDF) ? pigment_color<float>(ss.pigments, mat.brdf_pigment, u, v)
-                                                         : pig_c1<float>(ss.pigments[mat.brdf_pigment]);
+                V3<float> hit_color = (mf & MAT_UV_BRDF) ? pig_at(brdf_pig, u, v) : pig_uniform(brdf_pig);
                 const float lum = max3(hit_color);
                 bool go_on = true;
                 if (depth >= a.rr_limit) {  // render.py:116-123
@@ -350,11 +461,11 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
                 if (go_on && lum > 0.f) {
                   push = true;
                   V3<float> point, normal;
-                  world_frame<float>(im, ss.m + 12 * best, lh, sphere, true, point, normal);
-                  const V3<float> nd = (mat.brdf_kind == RT_BRDF_DIFFUSE) ? normal : specular_dir<float>(ray.d, normal);
+                  world_frame_rows(im, rows_of(false), lh, sphere, point, normal);
+                  const V3<float> nd = (brdf_kind == RT_BRDF_DIFFUSE) ? normal : specular_dir<float>(ray.d, normal);
                   const V3<float> w = inv_n * mul3(thr, hit_color);
                   out.a = make_float4(point.x, point.y, point.z,
-                                      __int_as_float(slot | (mat.brdf_kind << 5) | ((depth + 1) << 6) |
+                                      __int_as_float(slot | (brdf_kind << 5) | ((depth + 1) << 6) |
                                                      ((best < 0xFFFF ? best : 0xFFFF) << 16)));
                   out.b = make_float4(nd.x, nd.y, nd.z, w.x);
                   out.c = make_float4(w.y, w.z, __uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)));
@@ -387,7 +498,7 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
             col[0] += contrib.x; col[32] += contrib.y; col[64] += contrib.z;
           }
         } else {
-          sr += contrib.x; sg += contrib.y; sb += contrib.z;
+          sr += contrib.x; sg += contrib.y; sb_ += contrib.z;
         }
 
         // ---------------- push the new records: one ballot gives every lane its slot
@@ -395,14 +506,18 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
         const int npush = __popc(pmask);
         if (top + npush > cfg.cap) {
           overflow = true;
-        } else if (push) {
-          stack[top + __popc(pmask & ((1u << lane) - 1u))] = out;
+        } else {
+          if (push) {
+            const uint32_t pa = wb + (uint32_t)(top + __popc(pmask & ((1u << lane) - 1u))) * (uint32_t)sizeof(ScatterRec);
+            sts4(pa, out.a); sts4(pa + 16, out.b); sts4(pa + 32, out.c);
+          }
+          top += npush;
         }
-        if (top + npush <= cfg.cap) top += npush;
         __syncwarp();
         if (primary_phase && ++round >= cfg.rounds) primary_phase = false;
       }
     }
+    n_rays += task_rays;
 
     // ---------------- write the pixels of this task
     if (ACC == ACC_SEG) {
@@ -440,12 +555,12 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
       for (int d = 16; d > 0; d >>= 1) {
         sr += __shfl_xor_sync(FULL, sr, d);
         sg += __shfl_xor_sync(FULL, sg, d);
-        sb += __shfl_xor_sync(FULL, sb, d);
+        sb_ += __shfl_xor_sync(FULL, sb_, d);
       }
       if (lane == 0 && p0 < pm.n_pixels) {
         int col, row;
         pm.locate(p0, col, row);
-        store_pixel<float>(a, pm.at(p0, col, row), mk3<float>(sr * inv_spp, sg * inv_spp, sb * inv_spp));
+        store_pixel<float>(a, pm.at(p0, col, row), mk3<float>(sr * inv_spp, sg * inv_spp, sb_ * inv_spp));
         if (count_rays) a.out_hit[pm.at(p0, col, row)] = (int)task_rays;
       }
     }

@@ -225,17 +225,17 @@ k_pt_warp_bvh(const __grid_constant__ SceneView<float> sc, const __grid_constant
           const DevMaterial& mat = sc.materials[sc.material[best]];
           const int mf = mat.flags;
           const bool sphere = best < sc.n_spheres;
-          const float* im = sc.invm + 12 * (size_t)best;
+          const Rows3 im = rows_at(sc.invm + 12 * (size_t)best);  // the arithmetic of k_pt_warp, operation for operation
           float u = 0.f, v = 0.f;
           if (depth >= a.max_depth) {
             if (!(mf & MAT_EMIT_BLACK)) {
-              if (mf & MAT_UV_EMIT) local_uv<float>(local_hit<float>(im, ray, best_t), sphere, u, v);
+              if (mf & MAT_UV_EMIT) local_uv<float>(local_hit_rows(im, ray, best_t), sphere, u, v);
               contrib = mul3(thr, pigment_color<float>(sc.pigments, mat.emitted_pigment, u, v));
             }
           } else {
             const bool scatters = !(mf & MAT_NO_SCATTER);
             LocalHit<float> lh;
-            if (scatters || (mf & MAT_USES_UV)) lh = local_hit<float>(im, ray, best_t);
+            if (scatters || (mf & MAT_USES_UV)) lh = local_hit_rows(im, ray, best_t);
             if (mf & MAT_USES_UV) local_uv<float>(lh, sphere, u, v);
             if (!(mf & MAT_EMIT_BLACK)) contrib = mul3(thr, pigment_color<float>(sc.pigments, mat.emitted_pigment, u, v));
             if (scatters) {
@@ -253,7 +253,7 @@ k_pt_warp_bvh(const __grid_constant__ SceneView<float> sc, const __grid_constant
               if (go_on && lum > 0.f) {
                 push = true;
                 V3<float> point, normal;
-                world_frame<float>(im, sc.m + 12 * (size_t)best, lh, sphere, true, point, normal);
+                world_frame_rows(im, rows_at(sc.m + 12 * (size_t)best), lh, sphere, point, normal);
                 const V3<float> nd = (mat.brdf_kind == RT_BRDF_DIFFUSE) ? normal : specular_dir<float>(ray.d, normal);
                 const V3<float> w = inv_n * mul3(thr, hit_color);
                 out.a = make_float4(point.x, point.y, point.z,
