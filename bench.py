@@ -474,6 +474,12 @@ def roofline_of(sess, m, name):
             if prof.get(key + "_issue_slots_busy") is not None:
                 out["issue_slots_busy"] = prof.get(key + "_issue_slots_busy")
                 out["issue_slots_source"] = "smsp__issue_active.avg.pct_of_peak_sustained_active, profiles/traffic.json (committed ncu capture)"
+            for pipe in ("fma", "fp64"):
+                if prof.get(f"{key}_{pipe}_pipe_busy") is not None:
+                    out[f"{pipe}_pipe_busy"] = prof[f"{key}_{pipe}_pipe_busy"]
+                    out["pipe_busy_source"] = f"sm__pipe_{pipe}_cycles_active.avg.pct_of_peak_sustained_active, {prof.get(key + '_source', 'profiles/traffic.json')}"
+            if prof.get(key + "_thread_instructions_per_ray") is not None:
+                out["thread_instructions_per_ray"] = prof[key + "_thread_instructions_per_ray"]
             if prof.get(key + "_executed_flops_per_ray") is not None:
                 ex = prof[key + "_executed_flops_per_ray"]
                 out["executed_flops_per_ray"] = ex

@@ -17,7 +17,9 @@
 #include <cstdint>
 #include <vector>
 
-#define RT_BVH_LEAF 4
+#ifndef RT_BVH_LEAF
+#define RT_BVH_LEAF 1  // measured on B200 (profiles/r2_bvh_sweep.log): 1 | 2 | 4 spheres per leaf = 4.60 | 4.68 | 4.19 Grays/s on config 4, 7.36 | 6.98 | 6.70 on config 5 (fp64)
+#endif
 #define RT_BVH_SAH_DEPTH 20  // below this depth ranges are halved (balanced), so that the depth stays under
                              // RT_BVH_SAH_DEPTH + log2(n) < RT_BVH_STACK of rt_bvh.cuh for any scene that fits a GPU
 #define RT_BVH_BINS 16

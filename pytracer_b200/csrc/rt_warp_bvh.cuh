@@ -360,7 +360,7 @@ inline cudaError_t launch_pt_warp_bvh(const SceneView<float>& sc, const RenderAr
   cfg.inv_w = 1.0 / (double)a.width;
   cfg.inv_h = 1.0 / (double)a.height;
   cfg.inv_s = a.S > 0 ? 1.0 / (double)a.S : 1.0;
-  b.refill_at = 20;
+  b.refill_at = 16;
 #ifdef RT_TUNING
   if (const char* env = getenv("RT_BVH_REFILL_AT")) b.refill_at = atoi(env);
 #endif

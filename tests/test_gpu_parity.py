@@ -581,6 +581,14 @@ def test_config4_full_size_properties():
     rays_gpu = stats["rays_closest"] / stats["samples"]
     print(f"config 4: rays per sample GPU {rays_gpu:.2f}, oracle {ref_rays:.2f}; kernel {stats['kernel_ms']:.0f} ms")
     assert abs(rays_gpu - ref_rays) < 0.01 * ref_rays
+    # the same bars on a four times finer grid, 64x36 footprints of 60x60 pixels (6 912 values), against the
+    # committed oracle statistics (tests/golden/make_golden_c4.py: 16 runs x 16 spp, 75 M oracle rays)
+    fix = golden("c4_oracle_64x36.npz")
+    fine = img.reshape(36, 60, 64, 60, 3).mean(axis=(1, 3))
+    fine_ratio = 256.0 / (60 * 60 * 16)
+    assert_luminance_agreement(fine, fix["runs"], what="config 4, 60x60 footprints")
+    assert_mc_agreement(fine, fix["runs"], samples_ratio=fine_ratio, n_ref=256, what="config 4, 60x60 footprints")
+    assert abs(rays_gpu - float(fix["rays_per_sample"])) < 0.01 * float(fix["rays_per_sample"])
     # strata split over 8 ranks (2 strata each) sums to the frame
     acc = np.zeros_like(img)
     rays = 0
@@ -599,6 +607,8 @@ def test_config4_full_size_properties():
     assert np.allclose(small_b, small, rtol=2e-3, atol=1e-4)
     assert_luminance_agreement(small_b, ref, what="config 4 bvh, 120x120 footprints")
     assert_mc_agreement(small_b, ref, samples_ratio=ratio, n_ref=256, what="config 4 bvh, 120x120 footprints")
+    fine_b = rgb_b.astype(np.float64).reshape(36, 60, 64, 60, 3).mean(axis=(1, 3))
+    assert_mc_agreement(fine_b, fix["runs"], samples_ratio=fine_ratio, n_ref=256, what="config 4 bvh, 60x60 footprints")
 
 
 def test_config5_full_size_properties():

@@ -225,8 +225,10 @@ def _build_bvh(m):
 @pytest.mark.parametrize("n_spheres", [1, 2, 5, 64, 1024])
 def test_bvh_builder_invariants_and_conservative_boxes(n_spheres):
     """The tree rt_render walks with accel = bvh, built on the host: every sphere sits in exactly one leaf
-    of <= 4, every box contains its subtree's boxes, the leaf boxes contain the ellipsoids with the
+    of <= RT_BVH_LEAF spheres (rt_bvh.h), every box contains its subtree's boxes, the leaf boxes contain the ellipsoids with the
     documented padding, and a float64 walk of the tree finds every sphere a random ray really hits."""
+    header = open(os.path.join(ROOT, "pytracer_b200", "csrc", "rt_bvh.h")).read()
+    leaf_max = int(re.search(r"^#define RT_BVH_LEAF (\d+)", header, re.M).group(1))
     rs = scenes.random_spheres_scene(n_spheres, 11, 12, 15.0)
     fs = flatten_world(rs.world)
     sph = np.flatnonzero(fs.shape_kind == _abi.RT_SHAPE_SPHERE)
@@ -254,8 +256,8 @@ def test_bvh_builder_invariants_and_conservative_boxes(n_spheres):
                 clo, chi = subtree_box(int(ref))
             else:
                 first, count = leaf(ref)
-                assert count <= 4
-                if n_spheres <= 4 and c == 1:  # the never-hit second child that wraps a one-leaf scene
+                assert count <= leaf_max
+                if n_spheres <= leaf_max and c == 1:  # the never-hit second child that wraps a one-leaf scene
                     out.append((lo, hi))
                     continue
                 idx = prims[first:first + count]

@@ -175,3 +175,27 @@ def test_tonemap_oracle_matches_the_reference():
     out = tm.normalize_and_clamp(kat, factor=1000.0, luminosity_value=100.0)
     assert np.allclose(out / (1 - out), [[0.5e2, 1.0e2, 1.5e2], [0.5e4, 1.0e4, 1.5e4]])
     assert (out >= 0).all() and (out <= 1).all()
+
+
+def test_config4_oracle_fixture_is_reproducible():
+    """tests/golden/c4_oracle_64x36.npz (the statistics the full-size config-4 GPU test is held against) is
+    what the oracle computes: the rows of run 0 that thread 0 of oracle.render_threaded(…, 8) owns are
+    re-rendered here (its first two rows, 0 and 8, in its sequential stream order; 1 026 shapes: ~10 s)."""
+    from pytracer_b200 import _abi, scenes
+    from pytracer_b200.flatten import flatten_world
+    from pytracer_b200.pcg import PCG
+
+    fix = golden("c4_oracle_64x36.npz")
+    threads, spp = int(fix["threads"]), int(fix["spp_per_run"])
+    assert fix["runs"].shape == (16, 36, 64, 3) and spp == 16
+    rs = scenes.random_spheres_scene(1024, 2024, 4, 20.0)
+    fs = flatten_world(rs.world)
+    p = make_params(64, 36, rs.camera, algorithm="pathtracing", samples_per_side=4, num_of_rays=10, max_depth=3, rr_limit=3,
+                    aa_pcg=PCG(1000, 7), pt_pcg=PCG(2000, 9))
+    q = _abi.rt_render_params.from_buffer_copy(bytes(p))   # thread 0's streams, as render_threaded derives them
+    aa, pt = PCG(p.aa_state & 0xFFFFFFFF, 1000), PCG(p.pt_state & 0xFFFFFFFF, 2000)
+    q.aa_state, q.aa_inc, q.pt_state, q.pt_inc = aa.state, aa.inc, pt.state, pt.inc
+    r = oracle.render(fs, q, 0, threads + 1, want_hit=False, row_step=threads)
+    rows = [0, threads]
+    assert np.array_equal(r["rgb"][rows].astype(np.float32), fix["runs"][0][rows])
+    assert abs(float(fix["rays_per_sample"]) - 127.0) < 0.5
