@@ -99,52 +99,74 @@ def build_params(kw, camera, **extra):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: the sampler is started before the
+    warm-up (nvidia-smi takes a few hundred ms to deliver its first line) and only the samples whose
+    timestamps fall between `mark_begin()` and `mark_end()` are reported (all of them if none does)."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.proc, self.path = None, None
+        self.t0 = self.t1 = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "40"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
+        if self.t1 is None:
+            self.mark_end()
+        time.sleep(0.08)  # one more sampling period: the line of the last interval is on its way
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             for line in open(self.path):
                 parts = [x.strip() for x in line.split(",")]
-                if len(parts) < 7:
+                if len(parts) < 8:
                     continue
                 try:
-                    sm.append(float(parts[0]))
-                    mx.append(float(parts[1]))
+                    rows.append((self._stamp(parts[0]), float(parts[1]), float(parts[2]),
+                                 [n for n, val in zip(names, parts[4:8]) if val.lower().startswith("active")]))
                 except ValueError:
                     continue
-                for name, val in zip(names, parts[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if r[0] is not None and self.t0 is not None and self.t0 - 0.04 <= r[0] <= self.t1 + 0.04]
+        used = inside or rows
+        if used:
+            out = {"sm_mhz": statistics.median(r[1] for r in used), "sm_max_mhz": max(r[2] for r in used),
+                   "reasons": sorted({n for r in used for n in r[3]}), "samples": len(used),
+                   "window": "timed region" if inside else "whole run (no sample fell inside the timed region)"}
         return out
 
 
@@ -158,7 +180,8 @@ def cpu_baseline_sample(name, threads, width=None, height=None):
     world, camera, kw, _, _, n_sph = workload(name)
     flat = flatten_world(world)
     args = dict(kw)
-    args["samples_per_side"] = 1
+    # 1 sample per pixel on one thread; the threaded arm takes 4 (about 1.6 s per step on 16 threads instead of 0.4)
+    args["samples_per_side"] = 2 if (threads > 1 and n_sph <= 100 and not width) else 1
     if width:
         args["width"], args["height"] = width, height
     elif n_sph > 100:
@@ -168,7 +191,7 @@ def cpu_baseline_sample(name, threads, width=None, height=None):
     r = oracle.render_threaded(flat, p, threads) if threads > 1 else oracle.render(flat, p, want_hit=False)
     dt = time.perf_counter() - t0
     rays = r["rays_closest"] + r["rays_shadow"]
-    sample = f"{args['width']}x{args['height']} at 1 spp of the same scene/settings ({rays} rays, {dt:.1f} s)"
+    sample = f"{args['width']}x{args['height']} at {args['samples_per_side'] ** 2} spp of the same scene/settings ({rays} rays, {dt:.1f} s)"
     return rays / dt, sample
 
 
@@ -380,11 +403,13 @@ def measure_device(sess, name, steps, warmup, variant="auto", precision="auto", 
         def step():
             render_rows_allgather(scene, params, comm, slabs, sess.stream)
 
+    sampler = ClockSampler(sess.local_rank) if (sample_clocks and sess.rank == 0) else None
     for _ in range(max(warmup, 0)):
         step()
         scene.finish(sess.stream)
     sess.barrier()
-    sampler = ClockSampler(sess.local_rank) if (sample_clocks and sess.rank == 0) else None
+    if sampler:
+        sampler.mark_begin()
     events, rays_rank, kernel_ms, launches, st = [], 0, [], 0, {}
     wall0 = time.perf_counter()
     for _ in range(steps):
@@ -400,6 +425,8 @@ def measure_device(sess, name, steps, warmup, variant="auto", precision="auto", 
         launches += st["n_launches"]
     sess.barrier()
     wall = time.perf_counter() - wall0
+    if sampler:
+        sampler.mark_end()
     clocks = sampler.stop() if sampler else None
     total_ms = sess.reduce(sum(a.elapsed_time(b) for a, b in events), "max")
     rays = int(round(sess.reduce(float(rays_rank), "sum")))
