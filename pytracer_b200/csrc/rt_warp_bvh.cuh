@@ -160,14 +160,14 @@ k_pt_warp_bvh(const __grid_constant__ SceneView<float> sc, const __grid_constant
           thr = mk3<float>(rec.b.w, rec.c.x, rec.c.y);
           const uint64_t base = ((uint64_t)__float_as_uint(rec.c.w) << 32) | (uint64_t)__float_as_uint(rec.c.z);
           Pcg rng;
-          rng.state = mix64(base + (uint64_t)(child + 1) * 0x9E3779B97F4A7C15ULL);
+          rng.state = child_stream(base, child);
           rng.inc = a.pt_inc;
           ray.o = mk3<float>(rec.a.x, rec.a.y, rec.a.z);
           ray.tmax = Num<float>::inf();
           const V3<float> nd = mk3<float>(rec.b.x, rec.b.y, rec.b.z);
           if (((meta >> 5) & 1) == RT_BRDF_DIFFUSE) {
-            const float u1 = pcg_random_float<float>(rng);
-            const float u2 = pcg_random_float<float>(rng);
+            const float u1 = unit_from_u32((uint32_t)(rng.state >> 32));  // the two halves of the child's stream value
+            const float u2 = unit_from_u32((uint32_t)rng.state);
             ray.d = diffuse_dir<float>(nd, u1, u2);
             ray.tmin = 1.0e-3f;
           } else {
