@@ -245,6 +245,14 @@ int rt_bvh_build_host(const double* m, int32_t n_spheres, float* nodes_out, int3
  * (optional; shape hit by the LAST sample of each pixel, -1 = miss). Blocking. */
 int rt_render(rt_scene* scene, const rt_render_params* params, void* out_rgb,
               int32_t* out_hit_index, rt_stats* stats);
+/* The same image from ALL the devices of a node in one call, one process (the reference has
+ * no parallelism to replace — this is fire_all_rays again): scenes[i] = rt_scene_create() of the same World
+ * with device i current (rt_set_device).  Device i traces the interleaved rows i, i + n, ... and copies them
+ * into out_rgb / out_hit_index; the image is bit-identical to rt_render's on one device.  params->part_mode
+ * must be RT_PART_NONE.  stats: counters summed over the devices, kernel_ms / total_ms = the slowest device.
+ * Page-lock the host image (rt_host_register) so that the copies of the devices overlap. */
+int rt_render_multi(rt_scene* const* scenes, int32_t n_scenes, const rt_render_params* params, void* out_rgb,
+                    int32_t* out_hit_index, rt_stats* stats);
 /* Same with DEVICE buffers on a caller stream (cudaStream_t passed as void*; NULL = default
  * stream). Returns after enqueueing; call rt_render_finish() to synchronise the stream and
  * collect the counters. */

@@ -30,6 +30,7 @@ _PROTOTYPES = {
     "rt_bvh_build_host": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rt_scene_update_transforms": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
     "rt_render": (C.c_int, [_P, C.POINTER(_abi.rt_render_params), _P, _P, C.POINTER(_abi.rt_stats)]),
+    "rt_render_multi": (C.c_int, [C.POINTER(_P), C.c_int32, C.POINTER(_abi.rt_render_params), _P, _P, C.POINTER(_abi.rt_stats)]),
     "rt_render_device": (C.c_int, [_P, C.POINTER(_abi.rt_render_params), _P, _P, _P]),
     "rt_render_finish": (C.c_int, [_P, _P, C.POINTER(_abi.rt_stats)]),
     "rt_trace_rays": (C.c_int, [_P, C.POINTER(_abi.rt_render_params), _P, _P, C.c_int32, _P, _P]),

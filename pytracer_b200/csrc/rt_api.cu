@@ -617,8 +617,9 @@ extern "C" int rt_render_finish(rt_scene* s, void* stream, rt_stats* stats) {
   return RT_OK;
 }
 
-extern "C" int rt_render(rt_scene* s, const rt_render_params* p, void* out_rgb, int32_t* out_hit, rt_stats* stats) {
-  if (!s || !p || !out_rgb) return fail(RT_ERR_INVALID, "rt_render: null argument");
+// rt_render in two halves, so that rt_render_multi can have every device working before it waits for any:
+// enqueue = launch into the workspace image + the copy of the image (or of this rank's rows) to the host.
+static int render_enqueue(rt_scene* s, const rt_render_params* p, void* out_rgb, int32_t* out_hit) {
   CU(cudaSetDevice(s->device));
   if (p->width <= 0 || p->height <= 0) return fail(RT_ERR_INVALID, "image size %dx%d", p->width, p->height);
   if (p->n_peer_images != 0) return fail(RT_ERR_INVALID, "peer_images belong to rt_render_device");
@@ -633,31 +634,96 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, void* out_rgb, 
   int rc;
   if ((rc = ensure(&s->ws->image, &s->ws->image_cap, std::max<size_t>(bytes, 16))) != RT_OK) return rc;
   if (out_hit && (rc = ensure((void**)&s->ws->hit, &s->ws->hit_cap, std::max<size_t>(px * sizeof(int32_t), 16))) != RT_OK) return rc;
-  cudaEvent_t t0 = s->ws->t0, t1 = s->ws->t1;
-  CU(cudaEventRecord(t0, 0));
+  CU(cudaEventRecord(s->ws->t0, 0));
   rc = rt_render_device(s, p, s->ws->image, out_hit ? s->ws->hit : nullptr, nullptr);
-  if (rc == RT_OK) {
-    cudaError_t e = cudaSuccess;
-    if (!compact) {
-      e = cudaMemcpyAsync(out_rgb, s->ws->image, bytes, cudaMemcpyDeviceToHost, 0);
-      if (e == cudaSuccess && out_hit) e = cudaMemcpyAsync(out_hit, s->ws->hit, px * sizeof(int32_t), cudaMemcpyDeviceToHost, 0);
-    } else if (rows > 0) {
-      const size_t row_bytes = (size_t)p->width * px_bytes, hit_row = (size_t)p->width * sizeof(int32_t);
-      e = cudaMemcpy2DAsync((char*)out_rgb + (size_t)p->part_rank * row_bytes, (size_t)p->part_count * row_bytes, s->ws->image, row_bytes,
-                            row_bytes, rows, cudaMemcpyDeviceToHost, 0);
-      if (e == cudaSuccess && out_hit)
-        e = cudaMemcpy2DAsync((char*)out_hit + (size_t)p->part_rank * hit_row, (size_t)p->part_count * hit_row, s->ws->hit, hit_row, hit_row,
-                              rows, cudaMemcpyDeviceToHost, 0);
-    }
-    if (e == cudaSuccess) e = cudaEventRecord(t1, 0);
-    if (e != cudaSuccess) rc = fail(RT_ERR_CUDA, "image copy: %s", cudaGetErrorString(e));
+  if (rc != RT_OK) return rc;
+  cudaError_t e = cudaSuccess;
+  if (!compact) {
+    e = cudaMemcpyAsync(out_rgb, s->ws->image, bytes, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess && out_hit) e = cudaMemcpyAsync(out_hit, s->ws->hit, px * sizeof(int32_t), cudaMemcpyDeviceToHost, 0);
+  } else if (rows > 0) {
+    const size_t row_bytes = (size_t)p->width * px_bytes, hit_row = (size_t)p->width * sizeof(int32_t);
+    e = cudaMemcpy2DAsync((char*)out_rgb + (size_t)p->part_rank * row_bytes, (size_t)p->part_count * row_bytes, s->ws->image, row_bytes,
+                          row_bytes, rows, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess && out_hit)
+      e = cudaMemcpy2DAsync((char*)out_hit + (size_t)p->part_rank * hit_row, (size_t)p->part_count * hit_row, s->ws->hit, hit_row, hit_row,
+                            rows, cudaMemcpyDeviceToHost, 0);
   }
-  if (rc == RT_OK) rc = rt_render_finish(s, nullptr, stats);
+  if (e == cudaSuccess) e = cudaEventRecord(s->ws->t1, 0);
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, "image copy: %s", cudaGetErrorString(e));
+  return RT_OK;
+}
+
+static int render_collect(rt_scene* s, rt_stats* stats) {
+  int rc = rt_render_finish(s, nullptr, stats);
   if (rc == RT_OK && stats) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) stats->total_ms = ms;
+    if (cudaEventElapsedTime(&ms, s->ws->t0, s->ws->t1) == cudaSuccess) stats->total_ms = ms;
   }
   return rc;
+}
+
+extern "C" int rt_render(rt_scene* s, const rt_render_params* p, void* out_rgb, int32_t* out_hit, rt_stats* stats) {
+  if (!s || !p || !out_rgb) return fail(RT_ERR_INVALID, "rt_render: null argument");
+  int rc = render_enqueue(s, p, out_rgb, out_hit);
+  if (rc == RT_OK) rc = render_collect(s, stats);
+  return rc;
+}
+
+// One image over the devices of a node from ONE process and one call: scenes[i] is the same
+// World resident on device i; device i traces the rows i, i + n, ... (interleaved: the cost per row varies
+// widely) with the kernel it would run alone and copies exactly those rows into the caller's image.  Every
+// pixel is written by one device, so the image is bit-identical to the single-device image and no
+// collective is needed; all devices are launched before any is waited for.
+extern "C" int rt_render_multi(rt_scene* const* scenes, int32_t n_scenes, const rt_render_params* p, void* out_rgb,
+                               int32_t* out_hit, rt_stats* stats) {
+  if (!scenes || n_scenes < 1 || !p || !out_rgb) return fail(RT_ERR_INVALID, "rt_render_multi: null argument");
+  if (n_scenes > RT_MAX_PEERS * 8) return fail(RT_ERR_INVALID, "rt_render_multi: %d scenes", n_scenes);
+  for (int i = 0; i < n_scenes; ++i) {
+    if (!scenes[i]) return fail(RT_ERR_INVALID, "rt_render_multi: scene %d is null", i);
+    for (int j = 0; j < i; ++j)
+      if (scenes[j]->device == scenes[i]->device) return fail(RT_ERR_INVALID, "rt_render_multi: scenes %d and %d live on the same device", j, i);
+  }
+  if (n_scenes == 1) return rt_render(scenes[0], p, out_rgb, out_hit, stats);
+  if (p->part_mode != RT_PART_NONE) return fail(RT_ERR_INVALID, "rt_render_multi splits the image itself: part_mode must be RT_PART_NONE");
+  if (p->rng_mode == RT_RNG_REPLAY) return fail(RT_ERR_INVALID, "rt_render_multi: replay is a single-device mode");
+  int entry_device = 0;
+  CU(cudaGetDevice(&entry_device));
+  int rc = RT_OK, launched = 0;
+  for (int i = 0; i < n_scenes && rc == RT_OK; ++i) {
+    rt_render_params q = *p;
+    q.part_mode = RT_PART_ROWS;
+    q.part_rank = i;
+    q.part_count = n_scenes;
+    q.rows_layout = RT_ROWS_COMPACT;
+    rc = render_enqueue(scenes[i], &q, out_rgb, out_hit);
+    if (rc == RT_OK) launched = i + 1;
+  }
+  char first_error[sizeof(g_err)];
+  if (rc != RT_OK) memcpy(first_error, g_err, sizeof(g_err));
+  rt_stats total;
+  memset(&total, 0, sizeof(total));
+  for (int i = 0; i < launched; ++i) {  // every launched device is drained, also after an error
+    rt_stats st;
+    int r = render_collect(scenes[i], &st);
+    if (r != RT_OK) {
+      if (rc == RT_OK) { rc = r; memcpy(first_error, g_err, sizeof(g_err)); }
+      continue;
+    }
+    total.rays_closest += st.rays_closest;
+    total.rays_shadow += st.rays_shadow;
+    total.samples += st.samples;
+    total.overflow |= st.overflow;
+    total.n_launches += st.n_launches;
+    total.kernel_ms = std::max(total.kernel_ms, st.kernel_ms);
+    total.total_ms = std::max(total.total_ms, st.total_ms);
+    total.variant_used = st.variant_used;
+    total.precision_used = st.precision_used;
+  }
+  cudaSetDevice(entry_device);
+  if (rc != RT_OK) { memcpy(g_err, first_error, sizeof(g_err)); return rc; }
+  if (stats) *stats = total;
+  return RT_OK;
 }
 
 // ------------------------------------------------------------------------------------ probes
@@ -965,13 +1031,13 @@ extern "C" int rt_tone_map(const float* rgb, int64_t n_pixels, int32_t flags, do
 extern "C" int rt_host_register(void* ptr, uint64_t bytes) {
   if (!ptr || bytes == 0) return fail(RT_ERR_INVALID, "rt_host_register: bad argument");
   if (rt_device_count() <= 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
-  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);  // page-locked for every device of the process
   if (e == cudaErrorHostMemoryAlreadyRegistered) {
     // fine only if it is this very range that is registered (same caller pinning twice); an overlapping
     // older registration of a recycled address would leave part of the range pageable
     cudaGetLastError();
     cudaError_t u = cudaHostUnregister(ptr);
-    if (u == cudaSuccess) e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (u == cudaSuccess) e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
     else cudaGetLastError();
   }
   if (e != cudaSuccess) return fail(RT_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e));

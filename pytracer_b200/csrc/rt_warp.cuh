@@ -95,19 +95,21 @@ RT_DEV float4 lds4(uint32_t a) {  // read/write data (work stack): ordered again
 RT_DEV void sts4(uint32_t a, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-RT_DEV float4 lds4c(uint32_t a) {  // tables that are constant once staged: free to schedule and to merge
+// tables that are constant once staged: no "memory" clobber, so loads may move across ordinary memory
+// operations; volatile keeps them behind the __syncthreads() that ends the staging
+RT_DEV float4 lds4c(uint32_t a) {
   float4 v;
-  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
 RT_DEV int4 lds4ic(uint32_t a) {
   int4 v;
-  asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
   return v;
 }
 RT_DEV int ldsic(uint32_t a) {
   int v;
-  asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
 RT_DEV Rows3 lds_rows(uint32_t a) {

@@ -19,10 +19,13 @@ class DeviceScene:
     pigment / light tables, textures).  Build it from a World (ours or the reference's) or from a
     :class:`FlatScene`."""
 
-    def __init__(self, world_or_flat):
+    def __init__(self, world_or_flat, device: Optional[int] = None):
+        """``device``: the CUDA device the scene lives on (None = the current one)."""
         self._lib = _native.require_device()
         self.flat: FlatScene = world_or_flat if isinstance(world_or_flat, FlatScene) else flatten_world(world_or_flat)
         handle = C.c_void_p()
+        if device is not None:
+            _native.check(self._lib.rt_set_device(int(device)))
         _native.check(self._lib.rt_scene_create(C.byref(self.flat.desc), C.byref(handle)))
         self._handle = handle
 
@@ -122,6 +125,57 @@ class DeviceScene:
         out = np.zeros((inputs.shape[0], 8), dtype=np.float64)
         _native.check(self._lib.rt_scatter(self._handle, material, _abi.PRECISIONS[precision], _ptr(inputs), inputs.shape[0], _ptr(st), _ptr(out)))
         return out, int(st[0])
+
+
+class MultiDeviceScene:
+    """The same World resident on several devices of the node, rendered by ONE ``rt_render_multi`` call from
+    this process: device i traces the interleaved rows i, i + n, ... and copies them into the caller's
+    image; bit-identical to the single-device image (``CudaRenderer(..., gpus=n)``)."""
+
+    def __init__(self, world_or_flat, devices):
+        self._lib = _native.require_device()
+        devices = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+        available = self._lib.rt_device_count()
+        if not devices or len(set(devices)) != len(devices) or min(devices) < 0 or max(devices) >= available:
+            raise ValueError(f"devices {devices}: need distinct indices below the {available} visible device(s)")
+        self.flat: FlatScene = world_or_flat if isinstance(world_or_flat, FlatScene) else flatten_world(world_or_flat)
+        self.devices = devices
+        self.scenes = [DeviceScene(self.flat, device=d) for d in devices]
+        _native.check(self._lib.rt_set_device(devices[0]))
+
+    def close(self) -> None:
+        for s in self.scenes:
+            s.close()
+        self.scenes = []
+
+    def update_transforms(self, first: int, m: np.ndarray, invm: np.ndarray, stream: int = 0) -> None:
+        for s in self.scenes:
+            s.update_transforms(first, m, invm, stream)
+
+    def update_from_world(self, world, stream: int = 0) -> None:
+        new = world if isinstance(world, FlatScene) else flatten_world(world)
+        if not self.flat.differs_only_in_transforms(new):
+            raise ValueError("update_from_world: more than the transformations changed; build a new MultiDeviceScene")
+        for s in self.scenes:
+            s.update_transforms(0, new.shape_m, new.shape_invm, stream)
+
+    def render(self, params: _abi.rt_render_params, want_hit: bool = False, out: Optional[np.ndarray] = None,
+               replay_states: Optional[np.ndarray] = None) -> Tuple[np.ndarray, Optional[np.ndarray], dict]:
+        if replay_states is not None:
+            raise ValueError("replay is a single-device mode")
+        H, W = params.height, params.width
+        dtype = np.float64 if params.out_f64 else np.float32
+        if out is None:
+            out = np.empty((H, W, 3), dtype=dtype)
+        assert out.dtype == dtype and out.shape == (H, W, 3) and out.flags.c_contiguous
+        hit = np.empty((H, W), dtype=np.int32) if want_hit else None
+        handles = (C.c_void_p * len(self.scenes))(*[s._handle for s in self.scenes])
+        stats = _abi.rt_stats()
+        _native.check(self._lib.rt_render_multi(handles, len(self.scenes), C.byref(params), _ptr(out), _ptr(hit), C.byref(stats)))
+        return out, hit, stats.as_dict()
+
+    def trace_rays(self, *args, **kw):
+        return self.scenes[0].trace_rays(*args, **kw)
 
 
 # ---------------------------------------------------------------------- scene-free probes

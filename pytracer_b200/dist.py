@@ -7,7 +7,9 @@ random stream, and the scene (a few hundred bytes to ~200 KB) is replicated.  Tw
 * **rows** (default): rank r traces the image rows r, r + G, r + 2G, ... completely — interleaved,
   because the cost per row varies up to 85x on demo.txt.  Every rank runs the kernel it would run alone
   (one-pixel tasks, lane-private sums), each pixel is written by exactly one rank, and the N-GPU image
-  is bit-identical to the 1-GPU image.  What is left to exchange is placement, not arithmetic:
+  is bit-identical to the 1-GPU image (deterministic renderers always; path tracing from 32 samples per
+  pixel, where a warp's task is one pixel — below that pixels share a task, the grouping follows the
+  rank's own pixel list and a pixel's fp32 sum is formed in another order: equal to rounding).  What is left to exchange is placement, not arithmetic:
 
   - *host image* (``render_rows_to_shared_host``, what ``fire_all_rays(..., comm=)`` does): the ranks
     share ONE page-locked host image (POSIX shared memory registered with CUDA by every rank) and each

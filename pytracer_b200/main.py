@@ -80,13 +80,15 @@ def cli():
 @click.option("--precision", type=click.Choice(["auto", "f32", "f64"]), default="auto")
 @click.option("--parser", type=click.Choice(["auto", "reference", "builtin"]), default="auto")
 @click.option("--accel", type=click.Choice(["none", "bvh"]), default="none", help="bvh: sphere hierarchy, same image")
-@click.option("--gpus", type=int, default=1, help="GPUs of this node to render on (re-launches itself under torchrun)")
+@click.option("--gpus", type=int, default=1, help="GPUs of this node to render on: interleaved rows, one rt_render_multi call from this process")
+@click.option("--launcher", type=click.Choice(["inprocess", "torchrun"]), default="inprocess",
+              help="with --gpus N: drive the N devices from this process (default) or re-launch under torchrun, one process per GPU")
 @click.argument("input_scene_name", type=str)
 def render(width, height, algorithm, pfm_output, png_output, num_of_rays, max_depth, init_state, init_seq,
-           samples_per_pixel, declare_float, variant, precision, parser, accel, gpus, input_scene_name):
+           samples_per_pixel, declare_float, variant, precision, parser, accel, gpus, launcher, input_scene_name):
     import os
 
-    if gpus > 1 and "WORLD_SIZE" not in os.environ:  # one process per GPU: hand the same command line to torchrun
+    if gpus > 1 and launcher == "torchrun" and "WORLD_SIZE" not in os.environ:  # one process per GPU: hand the same command line to torchrun
         import socket
         import subprocess
 
@@ -105,6 +107,8 @@ def render(width, height, algorithm, pfm_output, png_output, num_of_rays, max_de
     print(f"Generating a {width}×{height} image")
     tracer = CudaImageTracer(image=image, camera=scene.camera, samples_per_side=samples_per_side)
     extra = dict(variant=variant, precision=precision, accel=accel)
+    if gpus > 1 and "WORLD_SIZE" not in os.environ:
+        extra["gpus"] = gpus
     if algorithm == "onoff":
         print("Using on/off renderer")
         renderer = OnOffRenderer(world=scene.world, background_color=BLACK, **extra)

@@ -16,7 +16,7 @@ from typing import Optional
 import numpy as np
 
 from . import _abi
-from .device import DeviceScene
+from .device import DeviceScene, MultiDeviceScene
 from .params import make_params
 from .pcg import PCG
 from .scene import BLACK, WHITE, Color, Ray
@@ -39,7 +39,10 @@ class CudaRenderer(Renderer):
     def __init__(self, world, background_color: Color = BLACK, algorithm: str = "pathtracing",
                  pcg: Optional[PCG] = None, num_of_rays: int = 10, max_depth: int = 10,
                  russian_roulette_limit: int = 3, ambient_color: Color = None, color: Color = WHITE,
-                 variant: str = "auto", precision: str = "auto", accel: str = "none"):
+                 variant: str = "auto", precision: str = "auto", accel: str = "none", gpus=1):
+        """``gpus``: how many devices of this node render an image (or a list of device indices), all from
+        this process and one ``rt_render_multi`` call per image — interleaved rows, the same image bit for bit.
+        (One process per GPU under ``torchrun`` is the other way: ``fire_all_rays(..., comm=)``.)"""
         super().__init__(world, background_color)
         if algorithm not in RENDERERS:
             raise ValueError(f"Unknown renderer: {algorithm}")
@@ -53,6 +56,7 @@ class CudaRenderer(Renderer):
         self.variant = variant
         self.precision = precision
         self.accel = accel  # "none": the reference's loop over all shapes; "bvh": sphere hierarchy (same image)
+        self.gpus = gpus
         self.last_stats: dict = {}
         self._scene: Optional[DeviceScene] = None
 
@@ -66,19 +70,25 @@ class CudaRenderer(Renderer):
 
         new = flatten_world(self.world)
         if self._scene is None:
-            self._scene = DeviceScene(new)
+            self._scene = self._new_scene(new)
         elif not self._scene.flat.differs_only_in_transforms(new):
             self._scene.close()
-            self._scene = DeviceScene(new)
+            self._scene = self._new_scene(new)
         elif not (np.array_equal(self._scene.flat.shape_m, new.shape_m) and np.array_equal(self._scene.flat.shape_invm, new.shape_invm)):
             self._scene.update_from_world(new)
         return self._scene
 
+    def _new_scene(self, flat):
+        multi = not isinstance(self.gpus, int) or self.gpus > 1
+        return MultiDeviceScene(flat, self.gpus) if multi else DeviceScene(flat)
+
     def refresh(self) -> None:
         """Flatten and upload the world again unconditionally."""
+        from .flatten import flatten_world
+
         if self._scene is not None:
             self._scene.close()
-        self._scene = DeviceScene(self.world)
+        self._scene = self._new_scene(flatten_world(self.world))
 
     def set_world(self, world) -> bool:
         """Next frame of an animation (the reference re-parses the scene with another `clock`,

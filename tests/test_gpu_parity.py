@@ -921,3 +921,47 @@ def test_every_kernel_at_tiny_sizes():
     import runpy, os
 
     runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), "kernel_sweep.py"))
+
+
+# ------------------------------------------------------------------ one process, several devices
+def test_single_process_multi_gpu_image_is_bit_identical():
+    """rt_render_multi / CudaRenderer(gpus=n): every visible device traces its interleaved rows from ONE
+    process and one call; image, hit index and counters equal the single-device render bit for bit (each pixel
+    is computed by exactly one device with the kernel it would run alone).  Needs >= 2 devices."""
+    from pytracer_b200 import _native
+    from pytracer_b200.device import MultiDeviceScene
+    from pytracer_b200.hdrimage import HdrImage
+    from pytracer_b200.imagetracer import CudaImageTracer
+    from pytracer_b200.render import PathTracer
+
+    n = _native.require_device().rt_device_count()
+    if n < 2:
+        pytest.skip("one visible device")
+    fs, cam = demo_flat()
+    one, many = DeviceScene(fs), MultiDeviceScene(fs, n)
+    # (path tracing: with >= 32 samples per pixel a warp's task is one pixel and the pixel's fp32 sum is formed
+    # in the same order wherever the pixel is traced; with fewer, pixels share a task, the grouping follows the
+    # device's own pixel list and the sum order differs: same samples, equal to fp32 rounding)
+    cases = [(dict(algorithm="pathtracing", samples_per_side=6, num_of_rays=4, max_depth=3, aa_pcg=PCG(42, 54), pt_pcg=PCG(45, 54)), True),
+             (dict(algorithm="pathtracing", samples_per_side=3, num_of_rays=4, max_depth=3, aa_pcg=PCG(42, 54), pt_pcg=PCG(45, 54)), False),
+             (dict(algorithm="pointlight", samples_per_side=2, aa_pcg=PCG(42, 54)), True),
+             (dict(algorithm="flat", samples_per_side=0, out_f64=True), True)]
+    for kw, exact in cases:
+        for w, h in ((203, 117), (64, n - 1)):  # odd sizes; fewer rows than devices
+            a, ha, sa = one.render(make_params(w, h, cam, **kw), want_hit=True)
+            b, hb, sb = many.render(make_params(w, h, cam, **kw), want_hit=True)
+            assert np.array_equal(ha, hb), (kw["algorithm"], w, h)
+            assert np.array_equal(a, b) if exact else np.allclose(a, b, rtol=1e-5, atol=1e-7), (kw["algorithm"], w, h)
+            assert (sa["rays_closest"], sa["rays_shadow"], sa["samples"]) == (sb["rays_closest"], sb["rays_shadow"], sb["samples"])
+    with pytest.raises(Exception):  # the call splits the image itself
+        many.render(make_params(64, 48, cam, "flat", 0, part_mode=_abi.RT_PART_ROWS, part_rank=0, part_count=2))
+    # through the public classes
+    world, camera = scenes.demo_scene()
+    imgs = []
+    for gpus in (1, n):
+        image = HdrImage(160, 120)
+        CudaImageTracer(image, camera, samples_per_side=6, pcg=PCG(42, 54)).fire_all_rays(
+            PathTracer(world, pcg=PCG(45, 54), num_of_rays=5, max_depth=3, gpus=gpus))
+        imgs.append(image.rgb_array().copy())
+    assert np.array_equal(imgs[0], imgs[1])
+    one.close(); many.close()
