@@ -20,7 +20,32 @@
 #pragma once
 #include "rt_warp.cuh"
 
+// Where a warp's scatter records live.  Shared memory (round 1) costs 7.7 KB per warp and, with the walk
+// stacks, holds the kernel to two blocks (16 warps) per SM — at 4 warps per scheduler the issue slots were
+// 52 % busy with `long_scoreboard` and `wait` on top (profiles/r2_c4_bvh_scaled4_full.csv): a latency-bound
+// kernel short of warps.  A record is read once per owed ray and written once per scattering hit, a few
+// bytes per hundred instructions of walking, so the stacks can live in GLOBAL memory (L2-resident, ld.cg /
+// st.cg) and the shared memory goes to a third block per SM.
+#ifndef RT_BVH_REC_GLOBAL
+#define RT_BVH_REC_GLOBAL 1
+#endif
+#ifndef RT_BVH_MINB
+#define RT_BVH_MINB (RT_BVH_REC_GLOBAL ? 3 : 2)
+#endif
+RT_DEV float4 rec_ld(const float4* p) { return RT_BVH_REC_GLOBAL ? __ldcg(p) : *p; }
+RT_DEV void rec_st(float4* p, float4 v) { if (RT_BVH_REC_GLOBAL) __stcg(p, v); else *p = v; }
+RT_DEV ScatterRec rec_load(const ScatterRec* r) {
+  ScatterRec v;
+  const float4* p = reinterpret_cast<const float4*>(r);
+  v.a = rec_ld(p); v.b = rec_ld(p + 1); v.c = rec_ld(p + 2);
+  return v;
+}
+RT_DEV void rec_store(ScatterRec* r, const ScatterRec& v) {
+  float4* p = reinterpret_cast<float4*>(r);
+  rec_st(p, v.a); rec_st(p + 1, v.b); rec_st(p + 2, v.c);
+}
 struct WarpBvhCfg {
+  ScatterRec* rec_pool;  // RT_BVH_REC_GLOBAL: (cap + 1) records per resident warp
   WarpCfg w;
   int refill_at;      // leave the walk phase when at most this many walks are still going
   int inner_min;      // leave the box-test loop for the sphere-test loop when at most this many lanes are descending
@@ -29,7 +54,7 @@ struct WarpBvhCfg {
   int n_nodes, n_prims;
 };
 
-__global__ void __launch_bounds__(RT_WARP_MAX_THREADS, 2)
+__global__ void __launch_bounds__(RT_WARP_MAX_THREADS, RT_BVH_MINB)
 k_pt_warp_bvh(const __grid_constant__ SceneView<float> sc, const __grid_constant__ RenderArgs a,
               const __grid_constant__ WarpBvhCfg bcfg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -46,9 +71,10 @@ k_pt_warp_bvh(const __grid_constant__ SceneView<float> sc, const __grid_constant
     tree.prims = reinterpret_cast<const int32_t*>(smem_raw + (size_t)bcfg.n_nodes * 64);
   }
   unsigned char* wbase = smem_raw + cfg.shape_bytes + warp * cfg.per_warp_bytes;
-  ScatterRec* stack = reinterpret_cast<ScatterRec*>(wbase);
+  ScatterRec* stack = RT_BVH_REC_GLOBAL ? bcfg.rec_pool + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)(cfg.cap + 1)
+                                        : reinterpret_cast<ScatterRec*>(wbase);
   ScatterRec* cur = stack + cfg.cap;
-  int* slot_rays = reinterpret_cast<int*>(cur + 1);       // [32]
+  int* slot_rays = RT_BVH_REC_GLOBAL ? reinterpret_cast<int*>(wbase) : reinterpret_cast<int*>(cur + 1);  // [32]
   float* acc = reinterpret_cast<float*>(slot_rays + 32);  // [G][3][32]
   float2* walk_stacks = reinterpret_cast<float2*>(acc + cfg.group * 96);  // [stack_entries][32]
   const bool count_rays = a.out_hit != nullptr && a.hit_mode == RT_HIT_RAY_COUNT;
@@ -127,13 +153,13 @@ k_pt_warp_bvh(const __grid_constant__ SceneView<float> sc, const __grid_constant
         int child = 0;
         if (get) {
           if (rank < from_cur) {
-            rec = *cur;
+            rec = rec_load(cur);
             child = cur_done + rank;
           } else {
             const int jj = rank - from_cur;
             const int r = div_n(jj);
             child = jj - r * N;
-            rec = stack[top - 1 - r];
+            rec = rec_load(&stack[top - 1 - r]);
           }
         }
         const int rest = take - from_cur;
@@ -143,7 +169,7 @@ k_pt_warp_bvh(const __grid_constant__ SceneView<float> sc, const __grid_constant
         __syncwarp();  // every lane has read its record
         int new_top = top - full;
         if (part > 0) {  // the next record is only partly consumed: it becomes `cur`
-          if (lane < 3) reinterpret_cast<float4*>(cur)[lane] = reinterpret_cast<const float4*>(&stack[new_top - 1])[lane];
+          if (lane < 3) rec_st(reinterpret_cast<float4*>(cur) + lane, rec_ld(reinterpret_cast<const float4*>(&stack[new_top - 1]) + lane));
           new_top -= 1;
           cur_rem = N - part;
           cur_done = part;
@@ -275,7 +301,7 @@ k_pt_warp_bvh(const __grid_constant__ SceneView<float> sc, const __grid_constant
       if (top + npush > cfg.cap) {
         overflow = true;
       } else if (push) {
-        stack[top + __popc(pmask & lt_mask)] = out;
+        rec_store(&stack[top + __popc(pmask & lt_mask)], out);
       }
       if (top + npush <= cfg.cap) top += npush;
       __syncwarp();
@@ -336,15 +362,15 @@ inline cudaError_t launch_pt_warp_bvh(const SceneView<float>& sc, const RenderAr
   b.stack_entries = tree_depth + 2;
   b.n_nodes = n_nodes;
   b.n_prims = n_prims;
-  // the tree itself goes to shared memory while two blocks still fit an SM with it
+  // the tree itself goes to shared memory while RT_BVH_MINB blocks still fit an SM with it
   const size_t tree_bytes = ((size_t)n_nodes * 64 + (size_t)n_prims * 4 + 15) / 16 * 16;
   const size_t limit = 200 * 1024;
   int warps = RT_WARP_MAX_THREADS / 32;
   size_t per_warp = 0, smem = 0;
   for (;; warps >>= 1) {
-    per_warp = (size_t)(cap + 1) * sizeof(ScatterRec) + 32 * sizeof(int) + (size_t)group * 96 * sizeof(float) +
+    per_warp = (RT_BVH_REC_GLOBAL ? 0 : (size_t)(cap + 1) * sizeof(ScatterRec)) + 32 * sizeof(int) + (size_t)group * 96 * sizeof(float) +
                (size_t)b.stack_entries * 32 * sizeof(float2);
-    b.tree_bytes = (tree_bytes + per_warp * warps <= 112 * 1024) ? (int)tree_bytes : 0;
+    b.tree_bytes = ((tree_bytes + per_warp * warps + 1024) * RT_BVH_MINB <= 227 * 1024) ? (int)tree_bytes : 0;
     smem = b.tree_bytes + per_warp * warps;
     if (smem <= limit || warps == 1) break;
   }
@@ -360,7 +386,7 @@ inline cudaError_t launch_pt_warp_bvh(const SceneView<float>& sc, const RenderAr
   cfg.inv_w = 1.0 / (double)a.width;
   cfg.inv_h = 1.0 / (double)a.height;
   cfg.inv_s = a.S > 0 ? 1.0 / (double)a.S : 1.0;
-  b.refill_at = 16;
+  b.refill_at = 12;  // measured with 24 warps per SM (profiles/r2_bvh_sweep2.log): 8 | 12 | 16 | 20 | 24 -> 6.14 | 6.17 | 6.12 | 5.98 | 5.87 Grays/s
 #ifdef RT_TUNING
   if (const char* env = getenv("RT_BVH_REFILL_AT")) b.refill_at = atoi(env);
 #endif
@@ -382,6 +408,23 @@ inline cudaError_t launch_pt_warp_bvh(const SceneView<float>& sc, const RenderAr
   long long blocks = (long long)per_sm * sm_count;  // persistent: every block stays resident
   long long needed = (cfg.n_tasks + warps - 1) / warps;
   if (blocks > needed) blocks = needed;
+  if (RT_BVH_REC_GLOBAL) {  // record stacks of all resident warps: one allocation per device, grown on demand
+    static ScatterRec* pool[64] = {nullptr};
+    static size_t pool_bytes[64] = {0};
+    int dev = 0;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const size_t bytes = (size_t)blocks * warps * (size_t)(cap + 1) * sizeof(ScatterRec);
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (bytes > pool_bytes[dev]) {
+      if (pool[dev]) { e = cudaDeviceSynchronize(); if (e == cudaSuccess) e = cudaFree(pool[dev]); if (e != cudaSuccess) return e; }  // (rare: a larger frame than ever before)
+      pool[dev] = nullptr; pool_bytes[dev] = 0;
+      e = cudaMalloc((void**)&pool[dev], bytes);
+      if (e != cudaSuccess) return e;
+      pool_bytes[dev] = bytes;
+    }
+    b.rec_pool = pool[dev];
+  }
   k_pt_warp_bvh<<<(unsigned)blocks, warps * 32, smem, st>>>(sc, a, b);
   if (info) { info->n_launches += 1; info->variant = RT_VARIANT_WARP; }
   return cudaGetLastError();
