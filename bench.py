@@ -11,9 +11,10 @@ scene resident in HBM and the image left in HBM, timed with CUDA events on the l
 ranks; `e2e` is the same metric through the public API (CudaImageTracer.fire_all_rays: flatten, scene
 upload, launch, device->host copy of the image into a page-locked host image) timed on the host clock,
 max over ranks.  With N > 1 the rows of the image are interleaved over the ranks (`scaling: strong` — the
-frame is fixed, the work is split): device-resident, one in-place NCCL all-gather of the row slabs is
-inside the timed region (`--exchange push` stores the pixels into every rank's image from inside the
-kernel instead; `--partition spp --exchange allreduce` is the strata split with one NCCL sum); end to end,
+frame is fixed, the work is split): device-resident, the render kernel stores every finished pixel into
+every rank's image over NVLink (symmetric memory) and a barrier closes the step (`--exchange allgather`:
+one in-place NCCL all-gather of the row slabs instead; `--partition spp`: the strata split with one NCCL
+sum); end to end,
 every rank copies its rows straight into one page-locked host image shared by the node.
 
 `--impl reference` times the reference's CPU implementation on all host threads: the C restatement
@@ -390,18 +391,26 @@ def measure_device(sess, name, steps, warmup, variant="auto", precision="auto", 
         def step():
             scene.render_device(p, image.data_ptr(), 0, sess.stream)
             comm.all_reduce_sum(image)
-    elif exchange == "push":
-        peers = PeerImages(H, W, comm)
-        part_name = "rows, pixels stored into every rank's image by the kernel (symmetric memory) + barrier"
-
-        def step():
-            render_rows_push(scene, params, comm, peers, sess.stream)
     else:
-        slabs = RowSlabs(H, W, G)
-        part_name = "rows + in-place all-gather of the row slabs"
+        peers, why = None, ""
+        if exchange == "push":
+            try:  # every rank must take the same branch: the outcome of the rendezvous is agreed on below
+                peers = PeerImages(H, W, comm)
+            except Exception as exc:
+                why = f"{type(exc).__name__}: {exc}"[:120]
+            if sess.reduce(0.0 if peers is not None else 1.0, "max") > 0.0:
+                peers, why = None, why or "the symmetric-memory rendezvous failed on another rank"
+        if peers is not None:
+            part_name = "rows, pixels stored into every rank's image by the kernel over NVLink (symmetric memory) + barrier"
 
-        def step():
-            render_rows_allgather(scene, params, comm, slabs, sess.stream)
+            def step():
+                render_rows_push(scene, params, comm, peers, sess.stream)
+        else:
+            slabs = RowSlabs(H, W, G)
+            part_name = "rows + in-place NCCL all-gather of the row slabs" + (f" (peer images unavailable: {why})" if why else "")
+
+            def step():
+                render_rows_allgather(scene, params, comm, slabs, sess.stream)
 
     sampler = ClockSampler(sess.local_rank) if (sample_clocks and sess.rank == 0) else None
     for _ in range(max(warmup, 0)):
@@ -563,6 +572,8 @@ def run_ours(args, rank, local_rank, world_size):
             configs["c5_bvh_auto_f64"] = sub_result(sess, "c5", 2, 1, 0, cpu=False, accel="bvh")
         else:
             configs["c3_spp_allreduce"] = sub_result(sess, "c3", args.steps, args.warmup, 0, cpu=False, partition="spp")
+            other = "allgather" if args.exchange == "push" else "push"
+            configs["c3_rows_" + other] = sub_result(sess, "c3", args.steps, args.warmup, 0, cpu=False, exchange=other)
             configs["c4_linear_rows"] = sub_result(sess, "c4", 1, 0, 1, cpu=False)
             configs["c5_auto_hybrid_rows"] = sub_result(sess, "c5", 2, 1, 2, cpu=False)
     if rank != 0:
@@ -598,9 +609,9 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "f32", "f64", "hybrid"])
     ap.add_argument("--partition", default="rows", choices=["rows", "spp"],
                     help="multi-GPU split: interleaved rows (default) or the strata of every pixel + one all-reduce")
-    ap.add_argument("--exchange", default="allgather", choices=["allgather", "push"],
-                    help="row split, device-resident arm: in-place NCCL all-gather of the row slabs, or stores into every "
-                         "rank's image from inside the kernel (symmetric memory)")
+    ap.add_argument("--exchange", default="push", choices=["allgather", "push"],
+                    help="row split, device-resident arm: stores into every rank's image from inside the kernel over NVLink "
+                         "(symmetric memory; the default: 514 vs 510 Grays/s on 8 GPUs), or an in-place NCCL all-gather of the row slabs")
     ap.add_argument("--accel", default="none", choices=["none", "bvh"],
                     help="bvh: sphere hierarchy instead of the reference's loop over all shapes (same image; separately reported mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
