@@ -576,6 +576,9 @@ def run_ours(args, rank, local_rank, world_size):
             configs["c3_rows_" + other] = sub_result(sess, "c3", args.steps, args.warmup, 0, cpu=False, exchange=other)
             configs["c4_linear_rows"] = sub_result(sess, "c4", 1, 0, 1, cpu=False)
             configs["c5_auto_hybrid_rows"] = sub_result(sess, "c5", 2, 1, 2, cpu=False)
+    if sess.comm is not None:  # unmap / unlink the node's shared host images (rank 0 owns the segments)
+        sess.barrier()
+        sess.comm.close()
     if rank != 0:
         return
     roofline = roofline_of(sess, m, name)

@@ -143,12 +143,15 @@ class SharedHostImage:
         except Exception:
             pass
         self.pinned = False
+        self.array = None
+        self.counters = self._flags = None
         try:
-            self.array = None
-            self.counters = self._flags = None
-            self._shm.close()
-            if self.rank == 0:
+            if self.rank == 0:  # the name goes away now; the memory when the last mapping does
                 self._shm.unlink()
+        except Exception:
+            pass
+        try:
+            self._shm.close()  # (raises while an image that adopted the frame is still alive: its mapping stays)
         except Exception:
             pass
 
