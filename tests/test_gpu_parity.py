@@ -965,3 +965,26 @@ def test_single_process_multi_gpu_image_is_bit_identical():
         imgs.append(image.rgb_array().copy())
     assert np.array_equal(imgs[0], imgs[1])
     one.close(); many.close()
+
+
+def test_render_command_with_gpus_writes_the_same_file(tmp_path):
+    """`render --gpus N` (all devices from this process): the PFM equals the single-device file byte for byte."""
+    from click.testing import CliRunner
+
+    from pytracer_b200 import _native
+    from pytracer_b200.main import cli
+
+    n = _native.require_device().rt_device_count()
+    if n < 2:
+        pytest.skip("one visible device")
+    scene_file = tmp_path / "demo.txt"
+    scene_file.write_text(DEMO_TEXT)
+    files = []
+    for gpus in (1, n):
+        pfm = tmp_path / f"g{gpus}.pfm"
+        res = CliRunner().invoke(cli, ["render", "--width", "200", "--height", "150", "--algorithm", "pointlight", "--samples-per-pixel", "4",
+                                       "--gpus", str(gpus), "--pfm-output", str(pfm), "--png-output", str(tmp_path / f"g{gpus}.png"),
+                                       "--parser", "builtin", str(scene_file)])
+        assert res.exit_code == 0, res.output
+        files.append(pfm.read_bytes())
+    assert files[0] == files[1]
